@@ -1,0 +1,169 @@
+/*
+ * include/spectral.h -- C-ABI of the B200-native planning hot path (libspectral.so).
+ *
+ * Plain C, no C++ or torch types, caller-owned buffers, int status returns, no exceptions
+ * across the boundary.  One handle per GPU; a handle is not thread-safe.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   find_traj()                 src/trp_wrapper.cpp:16-306 (libtrp.so), src/cub_wrapper.cpp:16-285
+ *                               (libcub.so): exported by our libtrp.so / libcub.so with the same
+ *                               signature, Params layout (include/btrapz/py_cpp_.h:6-21), hidden
+ *                               input/output files and return values, so src/trp_wrapper.py:45-54 and
+ *                               src/cub_wrapper.py load them unchanged.
+ *   spectral_solve_batch*()     the body of find_traj between parsing and cost for B scenarios at once:
+ *                               PiecewiseJerkSpeedProblem::CorridorGeneration (src/solve_3d.cc:323-486,
+ *                               src/cuboid_3d.cc:301-407), CorridorSplit (:729-772 / :588-625),
+ *                               CollisionCheck (:488-714 / :409-573), FormulateProblem (:1143-1229),
+ *                               Optimize (:1231-1414) incl. the OSQP solve it delegates to
+ *                               (osqp_setup/osqp_solve, :1246-1249) and the Bezier sampling (:1279-1392),
+ *                               and the wrapper cost (src/trp_wrapper.cpp:217-286).
+ *   spectral_argmin_device()    new (the reference has no batch): best trajectory of a sweep.
+ *   SpectralCube                struct Cube, include/btrapz/cube_type.h:2-24 (same 112-byte layout).
+ *   SpectralParams              struct Params, include/btrapz/py_cpp_.h:6-21 (same 88-byte layout).
+ */
+#ifndef SPECTRAL_H
+#define SPECTRAL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPECTRAL_TRP 0 /* trapezoid-prism corridors, reference libtrp.so (solve_3d.cc) */
+#define SPECTRAL_CUB 1 /* cuboid corridors, reference libcub.so (cuboid_3d.cc) */
+
+/* API return codes */
+#define SPECTRAL_SUCCESS 0
+#define SPECTRAL_ERR_INVALID 1
+#define SPECTRAL_ERR_CUDA 2
+#define SPECTRAL_ERR_CAPACITY 3
+
+/* per-scenario status[] values */
+#define SPECTRAL_SOLVED 0            /* OSQP status 1 */
+#define SPECTRAL_SOLVED_INACCURATE 1 /* OSQP status 2; the reference accepts it (solve_3d.cc:1253) */
+#define SPECTRAL_FAIL_NO_CORRIDOR 2  /* CollisionCheck selected nothing (reference: UB, solve_3d.cc:617) */
+#define SPECTRAL_FAIL_SOLVER 3       /* Optimize() == false -> find_traj returns 1e11 (trp_wrapper.cpp:199) */
+#define SPECTRAL_FAIL_POINTS_CHECK 4 /* CHECK_EQ(var_index, num_of_points_) would abort (solve_3d.cc:1407) */
+#define SPECTRAL_FAIL_TOO_MANY 5     /* more cubes/segments than the handle's capacity */
+
+/* per-scenario flags[] bits */
+#define SPECTRAL_FLAG_POLISHED_S 1 /* s-axis control points come from an accepted polish step */
+#define SPECTRAL_FLAG_POLISHED_L 2 /* l-axis likewise */
+#define SPECTRAL_FLAG_VERIFIED_S 4 /* s-axis control points satisfy the KKT conditions of the QP (exact optimum) */
+#define SPECTRAL_FLAG_VERIFIED_L 8 /* l-axis likewise */
+#define SPECTRAL_FLAG_VERIFIED (SPECTRAL_FLAG_VERIFIED_S | SPECTRAL_FLAG_VERIFIED_L)
+
+#define SPECTRAL_FAIL_COST 100000000000.0 /* the reference's failure sentinel */
+
+/* struct Cube (cube_type.h:2-24), 112 bytes */
+typedef struct {
+  int beg_t, end_t;
+  double t;
+  double t_dif;
+  double beg_l, end_l;
+  double upp_skew, upp_bias, down_skew, down_bias;
+  double l_upp_skew, l_upp_bias, l_down_skew, l_down_bias;
+  unsigned char merge, split;
+  int count;
+} SpectralCube;
+
+/* struct Params (py_cpp_.h:6-21), 88 bytes */
+typedef struct {
+  double s_acc_weight, s_jerk_weight, l_acc_weight, l_jerk_weight;
+  double weight_s_ref, weight_ds_ref, weight_l_ref, weight_dl_ref;
+  double weight_end_s, weight_end_l;
+  int iteration;
+} SpectralParams;
+
+/* Inputs of a batch of B scenarios sharing (N knots, R regions, delta_t).  All FP64, C-contiguous. */
+typedef struct {
+  const double *s_bounds;  /* [B][R][N][2]  (lo, hi) of s per region and knot  (set_x_bounds) */
+  const double *l_bounds;  /* [B][R][N][2]  (lo, hi) of l                      (set_y_bounds) */
+  const double *ds_bounds; /* [B][N][2]                                         (set_dx_bounds) */
+  const double *dl_bounds; /* [B][N][2]                                         (set_dy_bounds) */
+  const double *s_ref;     /* [B][N]                                            (set_x_ref) */
+  const double *l_ref;     /* [B][N]                                            (set_y_ref) */
+  const double *init;      /* [B][6]  s, ds, dds, l, dl, ddl at t = 0 */
+  const double *scalars;   /* [B][10] ds_ref, dl_ref, dds_lo, dds_hi, ddds_lo, ddds_hi, ddl_lo, ddl_hi, dddl_lo, dddl_hi */
+  const double *weights;   /* [B][10] or [1][10] in Params order (s_acc .. weight_end_l) */
+  int weights_stride;      /* 1: one weight vector per scenario; 0: one for the whole batch */
+} SpectralInputs;
+
+/* Outputs; any pointer except K/status may be NULL to skip it. */
+typedef struct {
+  int *K;             /* [B] segment count = new_corridor.size() */
+  SpectralCube *segs; /* [B][k_max] the selected corridor sequence */
+  double *ctrl;       /* [B][12*k_max]: s-axis control points [0,6K), l-axis [6K,12K) (OSQP x order) */
+  double *obj;        /* [B] QP objective 0.5 x'Px + q'x at ctrl */
+  double *a_cost;     /* [B] the wrapper's trajectory cost; 1e11 on failure */
+  int *status;        /* [B] SPECTRAL_SOLVED ... */
+  int *iters;         /* [B] ADMM iterations (max over the two axis problems) */
+  int *flags;         /* [B] SPECTRAL_FLAG_* */
+  int *npts;          /* [B] number of trajectory samples */
+  double *samples;    /* [B][samples_cap][6]: s, ds, dds, l, dl, ddl per sample */
+  int samples_cap;
+  double *lu;         /* debug: [B][2 axes][k_max][21][2] the QP's (l, u) rows per segment lane */
+} SpectralOutputs;
+
+typedef struct {
+  int max_iter;          /* 5000  (trp_wrapper.cpp:191) */
+  double eps_abs;        /* 1e-5  (solve_3d.cc:1239) */
+  double eps_rel;        /* 1e-5  (solve_3d.cc:1238) */
+  double eps_prim_inf;   /* 2.5e-5 (solve_3d.cc:1454) */
+  double rho;            /* 0.1   OSQP default */
+  double sigma;          /* 1e-6  OSQP default */
+  double alpha;          /* 1.6   OSQP default */
+  int scaling;           /* 4     (solve_3d.cc:1242) */
+  int check_termination; /* 25    OSQP default */
+  int adaptive_rho_interval; /* 100 = OSQP's fixed rule; 0 disables adaptation */
+  double adaptive_rho_tolerance; /* 5 */
+  int polish;            /* 1: refine the ADMM solution to the exact optimum of the identified active set */
+  double polish_delta;   /* 1e-6: regularisation of the active rows (OSQP's delta) */
+  int polish_refine_iter;/* 4 */
+  int polish_rounds;     /* 8: active-set correction rounds; a round that changes nothing verifies the KKT conditions */
+} SpectralOptions;
+
+typedef struct spectral_handle spectral_handle_t;
+
+void spectral_default_options(SpectralOptions *opt);
+
+/* device: CUDA ordinal.  Capacities: scenarios per call, knots, regions, segments (k_max <= 32). */
+int spectral_create(int device, int max_batch, int n_max, int r_max, int k_max, spectral_handle_t **out);
+int spectral_destroy(spectral_handle_t *h);
+const char *spectral_last_error(const spectral_handle_t *h);
+
+/* Host buffers: copies in, runs the device path, copies out, synchronises.  (The end-to-end path.) */
+int spectral_solve_batch(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                         const SpectralInputs *host_in, const SpectralOptions *opt,
+                         SpectralOutputs *host_out);
+
+/* Device buffers (already resident in HBM): enqueues on `cuda_stream` (a cudaStream_t, may be NULL)
+ * and returns without synchronising. */
+int spectral_solve_batch_device(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                const SpectralInputs *dev_in, const SpectralOptions *opt,
+                                SpectralOutputs *dev_out, void *cuda_stream);
+
+/* Best trajectory of a sweep: (min a_cost, lowest index on ties) over B device-resident costs.
+ * out_cost/out_index are DEVICE pointers (one double / one long long); index_offset is added to the
+ * local index so shards can be compared across ranks. */
+int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,
+                           double *out_cost_dev, long long *out_index_dev, void *cuda_stream);
+
+/* Number of kernel launches enqueued by this handle so far (for bench accounting). */
+long long spectral_launch_count(const spectral_handle_t *h);
+
+/* Measured FP64 FMA throughput of the device in TFLOP/s (micro-benchmark kernel; used as the
+ * roofline denominator of the ADMM kernel because MEASURED_PEAKS.json has no FP64 entry). */
+int spectral_measure_fp64_peak(spectral_handle_t *h, double *tflops);
+
+/* Device time (ms) spent in each kernel class during the last solve_batch*_ call with timing enabled. */
+#define SPECTRAL_NUM_KERNELS 6 /* tables, corridor, classify, qp, finalize, argmin */
+int spectral_set_timing(spectral_handle_t *h, int enabled);
+int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS]);
+
+/* The reference's plugin entry point (exported by libtrp.so / libcub.so, not by libspectral.so):
+ *   double find_traj(SpectralParams *p);                       trp_wrapper.cpp:20, cub_wrapper.cpp:19 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -238,7 +238,7 @@ void osqp_restate_default_settings(OsqpRestateSettings *s) {
   s->adaptive_rho_interval = 0; s->adaptive_rho_tolerance = 5.0; s->max_iter = 4000;
   s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
   s->alpha = 1.6; s->delta = 1e-6; s->polish = 0; s->polish_refine_iter = 3;
-  s->scaled_termination = 0; s->check_termination = 25;
+  s->scaled_termination = 0; s->check_termination = 25; s->polish_rounds = 1;
 }
 
 typedef struct {
@@ -480,65 +480,99 @@ static double compute_rho_estimate(Work *w) {
   return est;
 }
 
-/* -------------------------------------------------- polish (OSQP polish.c, restated dense-free) */
-static int polish(Work *w, double *pol_x, double *pol_y_full, int *n_active_out) {
+/* -------------------------------------------------- polish (OSQP polish.c, restated dense-free)
+ * One round is OSQP's polish: guess the active set from (z, y), solve the equality-constrained
+ * KKT system regularised by delta with iterative refinement.  With s->polish_rounds > 1 the
+ * active set is then CORRECTED (rows violated by the polished point are added, active rows whose
+ * multiplier has the wrong sign are dropped) and the solve repeated; when a round ends with no
+ * violated row and no wrong-signed multiplier the point satisfies the KKT conditions of the
+ * convex QP, i.e. it is the optimum: *verified = 1.  (This extension is only used for the
+ * CONVERGED oracle; the reference's own settings have polish = 0.) */
+static int polish(Work *w, double *pol_x, double *pol_y_full, int *n_active_out, int *verified) {
   ll n = w->n, m = w->m;
-  ll *ind = (ll *)malloc((m + 1) * sizeof(ll));
-  double *b = (double *)malloc((m + 1) * sizeof(double));
-  int *side = (int *)malloc((m + 1) * sizeof(int));
-  ll k = 0;
+  int *act = (int *)calloc(m + 1, sizeof(int)); /* -1 lower, +1 upper, 0 inactive */
   for (ll i = 0; i < m; i++) {
-    if (w->z[i] - w->l[i] < -w->y[i]) { ind[k] = i; b[k] = w->l[i]; side[k] = -1; k++; }
-    else if (w->u[i] - w->z[i] < w->y[i]) { ind[k] = i; b[k] = w->u[i]; side[k] = 1; k++; }
+    if (w->z[i] - w->l[i] < -w->y[i]) act[i] = -1;
+    else if (w->u[i] - w->z[i] < w->y[i]) act[i] = 1;
+    if (w->constr_type[i] == 1 && act[i] == 0) act[i] = -1; /* equality rows are always active */
   }
-  *n_active_out = (int)k;
-  /* A_red in CSC: rows renumbered */
+  ll *ind = (ll *)malloc((m + 1) * sizeof(ll));
   ll *rowmap = (ll *)malloc((m + 1) * sizeof(ll));
-  for (ll i = 0; i < m; i++) rowmap[i] = -1;
-  for (ll a = 0; a < k; a++) rowmap[ind[a]] = a;
-  Csc Ar; Ar.m = k; Ar.n = n;
+  double *b = (double *)malloc((m + 1) * sizeof(double));
+  double *rhs = (double *)malloc((n + m + 1) * sizeof(double));
+  double *px = (double *)malloc((n + 1) * sizeof(double));
+  double *xx = (double *)calloc(n + 1, sizeof(double));
+  double *yy = (double *)calloc(m + 1, sizeof(double));
+  double *ax = (double *)calloc(m + 1, sizeof(double));
+  double *dneg = (double *)malloc((m + 1) * sizeof(double));
+  Csc Ar; Ar.m = 0; Ar.n = n;
   Ar.p = (ll *)malloc((n + 1) * sizeof(ll));
   Ar.i = (ll *)malloc((w->A.nnz + 1) * sizeof(ll));
   Ar.x = (double *)malloc((w->A.nnz + 1) * sizeof(double));
-  ll nz = 0;
-  for (ll j = 0; j < n; j++) {
-    Ar.p[j] = nz;
-    for (ll p = w->A.p[j]; p < w->A.p[j + 1]; p++)
-      if (rowmap[w->A.i[p]] >= 0) { Ar.i[nz] = rowmap[w->A.i[p]]; Ar.x[nz] = w->A.x[p]; nz++; }
-  }
-  Ar.p[n] = nz; Ar.nnz = nz;
-  double delta = w->s->delta;
-  double *dneg = (double *)malloc((k + 1) * sizeof(double));
-  for (ll a = 0; a < k; a++) dneg[a] = -delta;
-  Kkt K; Ldl F; memset(&F, 0, sizeof(F));
-  kkt_build(&K, &w->P, &Ar, delta, dneg, n, k);
-  ldl_symbolic(&F, K.dim, K.p, K.i);
-  int ok = ldl_numeric(&F, K.p, K.i, K.x) == 0;
-  double *sol = (double *)calloc(n + k + 1, sizeof(double));  /* [y_red ; x] in KKT ordering */
-  double *rhs = (double *)malloc((n + k + 1) * sizeof(double));
-  double *px = (double *)malloc((n + 1) * sizeof(double));
-  double *xx = (double *)calloc(n + 1, sizeof(double));
-  double *yy = (double *)calloc(k + 1, sizeof(double));
-  if (ok) {
-    for (int it = 0; it <= w->s->polish_refine_iter; it++) {
-      /* residual of the UNREGULARISED system: [-q - P x - Ar' y ; b - Ar x] */
-      sym_mat_vec(&w->P, xx, px);
-      mat_tpose_vec(&Ar, yy, w->tmp_n, 0);
-      for (ll j = 0; j < n; j++) rhs[k + j] = -w->q[j] - px[j] - w->tmp_n[j];
-      for (ll a = 0; a < k; a++) rhs[a] = b[a];
-      for (ll j = 0; j < n; j++)
-        for (ll p = Ar.p[j]; p < Ar.p[j + 1]; p++) rhs[Ar.i[p]] -= Ar.x[p] * xx[j];
-      ldl_solve(&F, rhs);
-      for (ll a = 0; a < k; a++) yy[a] += rhs[a];
-      for (ll j = 0; j < n; j++) xx[j] += rhs[k + j];
+  int ok = 1, rounds = w->s->polish_rounds > 0 ? (int)w->s->polish_rounds : 1;
+  *verified = 0;
+  ll k = 0;
+  for (int round = 0; round < rounds && ok; round++) {
+    k = 0;
+    for (ll i = 0; i < m; i++) {
+      rowmap[i] = -1;
+      if (act[i]) { ind[k] = i; b[k] = act[i] < 0 ? w->l[i] : w->u[i]; rowmap[i] = k; k++; }
     }
+    ll nz = 0;
+    for (ll j = 0; j < n; j++) {
+      Ar.p[j] = nz;
+      for (ll p = w->A.p[j]; p < w->A.p[j + 1]; p++)
+        if (rowmap[w->A.i[p]] >= 0) { Ar.i[nz] = rowmap[w->A.i[p]]; Ar.x[nz] = w->A.x[p]; nz++; }
+    }
+    Ar.p[n] = nz; Ar.nnz = nz; Ar.m = k;
+    double delta = w->s->delta;
+    for (ll a = 0; a < k; a++) dneg[a] = -delta;
+    Kkt K; Ldl F; memset(&F, 0, sizeof(F));
+    kkt_build(&K, &w->P, &Ar, delta, dneg, n, k);
+    ldl_symbolic(&F, K.dim, K.p, K.i);
+    ok = ldl_numeric(&F, K.p, K.i, K.x) == 0;
+    if (ok) {
+      for (ll j = 0; j < n; j++) xx[j] = 0.0;
+      for (ll a = 0; a < k; a++) yy[a] = 0.0;
+      for (int it = 0; it <= w->s->polish_refine_iter; it++) {
+        /* residual of the UNREGULARISED system: [-q - P x - Ar' y ; b - Ar x] */
+        sym_mat_vec(&w->P, xx, px);
+        mat_tpose_vec(&Ar, yy, w->tmp_n, 0);
+        for (ll j = 0; j < n; j++) rhs[k + j] = -w->q[j] - px[j] - w->tmp_n[j];
+        for (ll a = 0; a < k; a++) rhs[a] = b[a];
+        for (ll j = 0; j < n; j++)
+          for (ll p = Ar.p[j]; p < Ar.p[j + 1]; p++) rhs[Ar.i[p]] -= Ar.x[p] * xx[j];
+        ldl_solve(&F, rhs);
+        for (ll a = 0; a < k; a++) yy[a] += rhs[a];
+        for (ll j = 0; j < n; j++) xx[j] += rhs[k + j];
+      }
+    }
+    kkt_free(&K); ldl_free(&F);
+    if (!ok) break;
+    /* KKT check of the polished point and active-set correction */
+    mat_vec(&w->A, xx, ax, 0);
+    double nax = vmax_abs(ax, m), ny = vmax_abs(yy, k);
+    double tol_p = 1e-9 * (1.0 + nax), tol_d = 1e-9 * (1.0 + ny);
+    int changed = 0;
+    for (ll i = 0; i < m; i++) {
+      if (!act[i]) {
+        if (ax[i] < w->l[i] - tol_p) { act[i] = -1; changed++; }
+        else if (ax[i] > w->u[i] + tol_p) { act[i] = 1; changed++; }
+      } else if (w->constr_type[i] != 1) {
+        double yi = yy[rowmap[i]];
+        if ((act[i] < 0 && yi > tol_d) || (act[i] > 0 && yi < -tol_d)) { act[i] = 0; changed++; }
+      }
+    }
+    if (!changed) { *verified = 1; break; }
+  }
+  if (ok) {
     for (ll j = 0; j < n; j++) pol_x[j] = xx[j];
     for (ll i = 0; i < m; i++) pol_y_full[i] = 0.0;
     for (ll a = 0; a < k; a++) pol_y_full[ind[a]] = yy[a];
   }
-  (void)side; (void)sol;
-  free(sol); free(rhs); free(px); free(xx); free(yy); free(dneg);
-  kkt_free(&K); ldl_free(&F); csc_free(&Ar); free(rowmap); free(ind); free(b); free(side);
+  *n_active_out = (int)k;
+  free(rhs); free(px); free(xx); free(yy); free(ax); free(dneg);
+  csc_free(&Ar); free(rowmap); free(ind); free(b); free(act);
   return ok ? 0 : -1;
 }
 
@@ -629,8 +663,8 @@ done:
   if ((status == OSQP_RESTATE_SOLVED || status == OSQP_RESTATE_SOLVED_INACCURATE) && s->polish) {
     double *px_ = (double *)malloc((n + 1) * sizeof(double));
     double *py_ = (double *)malloc((m + 1) * sizeof(double));
-    int nact = 0;
-    if (polish(w, px_, py_, &nact) == 0) {
+    int nact = 0, verified = 0;
+    if (polish(w, px_, py_, &nact, &verified) == 0) {
       /* accept iff the polished point has smaller (scaled) residuals than the ADMM point */
       double *sx = w->x, *sy = w->y, *sz = w->z;
       double *pz = (double *)malloc((m + 1) * sizeof(double));
@@ -642,7 +676,7 @@ done:
       compute_res(w, &p1, &d1, &a, &b2);
       if ((p1 < p0 && d1 < d0) || (p1 < p0 && d0 < 1e-10) || (d1 < d0 && p0 < 1e-10)) {
         memcpy(sx, px_, n * sizeof(double)); memcpy(sy, py_, m * sizeof(double)); memcpy(sz, pz, m * sizeof(double));
-        info->polish_status = 1; pri = p1; dua = d1;
+        info->polish_status = verified ? 2 : 1; pri = p1; dua = d1;
       } else info->polish_status = -1;
       w->x = sx; w->y = sy; w->z = sz;
       free(pz);

@@ -24,10 +24,11 @@ typedef struct {
   long long max_iter;
   double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, alpha, delta;
   long long polish, polish_refine_iter, scaled_termination, check_termination;
+  long long polish_rounds; /* >1: active-set correction rounds with KKT verification (extension) */
 } OsqpRestateSettings;
 
 typedef struct {
-  int status, iter, rho_updates, polish_status, n_active;
+  int status, iter, rho_updates, polish_status /* 0 none, 1 accepted, 2 accepted + KKT-verified, -1 rejected */, n_active;
   double obj_val, pri_res, dua_res, rho_final;
 } OsqpRestateInfo;
 

@@ -65,12 +65,14 @@ c_int osqp_solve(OSQPWorkspace *w) {
   r.eps_prim_inf = s->eps_prim_inf; r.eps_dual_inf = s->eps_dual_inf; r.alpha = s->alpha;
   r.delta = s->delta; r.polish = s->polish; r.polish_refine_iter = s->polish_refine_iter;
   r.scaled_termination = s->scaled_termination; r.check_termination = s->check_termination;
+  r.polish_rounds = 1;
   if (g_ovr.active) {
     if (g_ovr.eps > 0) { r.eps_abs = g_ovr.eps; r.eps_rel = g_ovr.eps; }
     if (g_ovr.max_iter > 0) r.max_iter = g_ovr.max_iter;
     r.polish = g_ovr.polish;
     if (g_ovr.delta > 0) r.delta = g_ovr.delta;
     if (g_ovr.polish_refine_iter > 0) r.polish_refine_iter = g_ovr.polish_refine_iter;
+    if (g_ovr.polish_rounds > 0) r.polish_rounds = g_ovr.polish_rounds;
   }
   OsqpRestateInfo info;
   osqp_restate_solve(d->n, d->m, d->P->p, d->P->i, d->P->x, d->q, d->A->p, d->A->i, d->A->x,

@@ -17,6 +17,7 @@ typedef struct {
   long long polish;
   double delta;
   long long polish_refine_iter;
+  long long polish_rounds;
 } SpectralShimOverride;
 SpectralShimLast *spectral_shim_last(void);
 void spectral_shim_set_override(const SpectralShimOverride *o);

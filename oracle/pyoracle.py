@@ -73,20 +73,21 @@ def solve_batch(variant, batch, weights, mode=0, k_max=32, nthreads=1, kind="por
     iters = np.zeros(B, np.int32)
     npts = np.zeros(B, np.int32)
     samples = np.zeros((B, samples_cap, 6))
+    polish = np.zeros(B, np.int32)
     lib = load(kind, variant)
     vid = VARIANT_ID[variant]
     common = [ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(R), ctypes.c_double(batch.delta_t)] + \
         [_d(a) for a in arrs] + [_d(w), ctypes.c_int(stride), ctypes.c_int(mode), ctypes.c_int(k_max),
                                  ctypes.c_int(nthreads), _i(K), segs.ctypes.data_as(ctypes.c_void_p), _d(ctrl),
                                  _d(obj), _d(a_cost), _i(status), _i(iters), _i(npts), _d(samples),
-                                 ctypes.c_int(samples_cap)]
+                                 ctypes.c_int(samples_cap), _i(polish)]
     if kind == "port":
         lib.oracle_solve_batch(ctypes.c_int(vid), *common)
     else:
         assert lib.ref_variant() == vid
         lib.ref_solve_batch(*common)
     return dict(K=K, segs=segs, ctrl=ctrl, obj=obj, a_cost=a_cost, status=status, iters=iters, npts=npts,
-                samples=samples)
+                samples=samples, polish=polish)
 
 
 class _QP(ctypes.Structure):

@@ -70,7 +70,7 @@ extern "C" int ref_solve_batch(int B, int N, int R, double delta, const double *
                                int weights_stride, int mode, int k_max, int nthreads, int *K,
                                OracleCube *segs, double *ctrl, double *obj, double *a_cost,
                                int *status, int *iters, int *npts, double *samples,
-                               int samples_cap) {
+                               int samples_cap, int *polish) {
   std::ios_base::iostate old_state = std::cout.rdstate();
   std::cout.setstate(std::ios_base::failbit); /* silence the reference's debug prints */
 #ifdef _OPENMP
@@ -89,6 +89,7 @@ extern "C" int ref_solve_batch(int B, int N, int R, double delta, const double *
     std::memset(ct, 0, sizeof(double) * 12 * (size_t)k_max);
     K[b] = 0; obj[b] = 0; a_cost[b] = 100000000000.0; iters[b] = 0; status[b] = ORACLE_FAIL_SOLVER;
     if (npts) npts[b] = 0;
+    if (polish) polish[b] = 0;
 
     /* ---- guards, predicted with the restatement */
     OracleProblem p;
@@ -160,7 +161,7 @@ extern "C" int ref_solve_batch(int B, int N, int R, double delta, const double *
       /* converged optimum through the same reference code path: tighten until the polish is accepted.
        * A fresh problem object is needed per attempt (num_of_points_ accumulates in Optimize). */
       static const double ladder[3] = {1e-6, 1e-8, 1e-10};
-      ovr.active = 1; ovr.max_iter = 50000; ovr.polish = 1; ovr.delta = 1e-9; ovr.polish_refine_iter = 8;
+      ovr.active = 1; ovr.max_iter = 50000; ovr.polish = 1; ovr.delta = 1e-9; ovr.polish_refine_iter = 8; ovr.polish_rounds = 12;
       ovr.eps = ladder[0];
       spectral_shim_set_override(&ovr);
       ok = prob.Optimize(5000);
@@ -169,6 +170,7 @@ extern "C" int ref_solve_batch(int B, int N, int R, double delta, const double *
     }
     SpectralShimLast *last = spectral_shim_last();
     iters[b] = last->iter;
+    if (polish) polish[b] = last->polish_status;
     if (!ok) { status[b] = ORACLE_FAIL_SOLVER; continue; }
     std::memcpy(ct, last->x, sizeof(double) * 12 * (size_t)kk);
     obj[b] = last->obj_val;

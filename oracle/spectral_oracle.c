@@ -825,11 +825,11 @@ int oracle_find_traj_mem(int variant, const OracleProblem *p, int R, const doubl
   } else {
     /* converged optimum: tighten until the polish is accepted */
     static const double eps_ladder[3] = {1e-6, 1e-8, 1e-10};
-    s.polish = 1; s.delta = 1e-9; s.polish_refine_iter = 8; s.max_iter = 50000;
+    s.polish = 1; s.delta = 1e-9; s.polish_refine_iter = 8; s.max_iter = 50000; s.polish_rounds = 12;
     for (int a = 0; a < 3; a++) {
       s.eps_abs = s.eps_rel = eps_ladder[a];
       osqp_restate_solve(qp.n, qp.m, qp.P_p, qp.P_i, qp.P_x, qp.q, qp.A_p, qp.A_i, qp.A_x, qp.l, qp.u, &s, x, NULL, &info);
-      if (info.polish_status == 1 || !(info.status == 1 || info.status == 2)) break;
+      if (info.polish_status == 2 || !(info.status == 1 || info.status == 2)) break;
     }
   }
   res->iters = info.iter;
@@ -857,7 +857,7 @@ int oracle_solve_batch(int variant, int B, int N, int R, double delta, const dou
                        const double *scalars, const double *weights, int weights_stride,
                        int mode, int k_max, int nthreads, int *K, OracleCube *segs, double *ctrl,
                        double *obj, double *a_cost, int *status, int *iters, int *npts,
-                       double *samples, int samples_cap) {
+                       double *samples, int samples_cap, int *polish) {
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #else
@@ -888,6 +888,7 @@ int oracle_solve_batch(int variant, int B, int N, int R, double delta, const dou
                          mode, k_max, sg, ct, smp, cap, &r);
     K[b] = r.K; obj[b] = r.obj; a_cost[b] = r.a_cost; status[b] = r.status; iters[b] = r.iters;
     if (npts) npts[b] = r.npts;
+    if (polish) polish[b] = r.polish_status;
     if (!samples) free(smp);
   }
   return 0;

@@ -99,7 +99,7 @@ int oracle_solve_batch(int variant, int B, int N, int R, double delta, const dou
                        const double *scalars, const double *weights, int weights_stride,
                        int mode, int k_max, int nthreads, int *K, OracleCube *segs, double *ctrl,
                        double *obj, double *a_cost, int *status, int *iters, int *npts,
-                       double *samples, int samples_cap);
+                       double *samples, int samples_cap, int *polish /* 2 = KKT-verified optimum */);
 
 #ifdef __cplusplus
 }

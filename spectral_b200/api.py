@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's plugin interface on top of the C-ABI (include/spectral.h).
+
+* ``SpectralPlanner``       one handle per GPU around ``libspectral.so`` -- batch entry points
+  (host buffers = the end-to-end path; device tensors = the resident path; argmin).
+* ``Params`` / ``find_traj`` / ``run_btrapz``  the same names, argument meaning and return values as
+  the reference's ``src/trp_wrapper.py:19-32,56-121`` (``cub_wrapper.py`` likewise), bound to OUR
+  ``libtrp.so`` / ``libcub.so``.
+
+There is no CPU path: importing works anywhere, but creating a planner or calling ``find_traj``
+without the built libraries or without a CUDA device raises.  PyTorch is used only for device
+memory / streams by ``solve_device``; it is imported lazily.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .wire import ScenarioBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+
+TRP, CUB = 0, 1
+VARIANT_ID = {"trp": TRP, "cub": CUB, TRP: TRP, CUB: CUB}
+
+SOLVED, SOLVED_INACCURATE, FAIL_NO_CORRIDOR, FAIL_SOLVER, FAIL_POINTS_CHECK, FAIL_TOO_MANY = range(6)
+FLAG_POLISHED_S, FLAG_POLISHED_L, FLAG_VERIFIED_S, FLAG_VERIFIED_L = 1, 2, 4, 8
+FLAG_VERIFIED = FLAG_VERIFIED_S | FLAG_VERIFIED_L
+FAIL_COST = 100000000000.0
+NUM_KERNELS = 6
+KERNEL_NAMES = ("tables", "corridor", "classify", "qp", "finalize", "argmin")
+
+CUBE_DTYPE = np.dtype([
+    ("beg_t", np.int32), ("end_t", np.int32), ("t", np.float64), ("t_dif", np.float64),
+    ("beg_l", np.float64), ("end_l", np.float64), ("upp_skew", np.float64), ("upp_bias", np.float64),
+    ("down_skew", np.float64), ("down_bias", np.float64), ("l_upp_skew", np.float64),
+    ("l_upp_bias", np.float64), ("l_down_skew", np.float64), ("l_down_bias", np.float64),
+    ("merge", np.uint8), ("split", np.uint8), ("_pad", np.uint8, (2,)), ("count", np.int32)])
+assert CUBE_DTYPE.itemsize == 112  # struct Cube, include/btrapz/cube_type.h:2-24
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+class SpectralInputs(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init",
+                                   "scalars", "weights")] + [("weights_stride", ctypes.c_int)]
+
+
+class SpectralOutputs(ctypes.Structure):
+    _fields_ = [("K", _ip), ("segs", ctypes.c_void_p), ("ctrl", _dp), ("obj", _dp), ("a_cost", _dp), ("status", _ip),
+                ("iters", _ip), ("flags", _ip), ("npts", _ip), ("samples", _dp), ("samples_cap", ctypes.c_int),
+                ("lu", _dp)]
+
+
+class SpectralOptions(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int), ("eps_abs", ctypes.c_double), ("eps_rel", ctypes.c_double),
+                ("eps_prim_inf", ctypes.c_double), ("rho", ctypes.c_double), ("sigma", ctypes.c_double),
+                ("alpha", ctypes.c_double), ("scaling", ctypes.c_int), ("check_termination", ctypes.c_int),
+                ("adaptive_rho_interval", ctypes.c_int), ("adaptive_rho_tolerance", ctypes.c_double),
+                ("polish", ctypes.c_int), ("polish_delta", ctypes.c_double), ("polish_refine_iter", ctypes.c_int),
+                ("polish_rounds", ctypes.c_int)]
+
+
+class Params(ctypes.Structure):
+    """struct Params of include/btrapz/py_cpp_.h:6-21 == class Params of src/trp_wrapper.py:19-32."""
+    _fields_ = [("s_acc_weight", ctypes.c_double), ("s_jerk_weight", ctypes.c_double),
+                ("l_acc_weight", ctypes.c_double), ("l_jerk_weight", ctypes.c_double),
+                ("weight_s_ref", ctypes.c_double), ("weight_ds_ref", ctypes.c_double),
+                ("weight_l_ref", ctypes.c_double), ("weight_dl_ref", ctypes.c_double),
+                ("weight_end_s", ctypes.c_double), ("weight_end_l", ctypes.c_double), ("iteration", ctypes.c_int)]
+
+
+_lib = None
+
+
+def lib_path(name: str = "libspectral.so") -> str:
+    return os.path.join(LIB_DIR, name)
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libspectral.so; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                           "`make -C spectral_b200/csrc` (there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    lib.spectral_create.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_void_p)]
+    lib.spectral_destroy.argtypes = [ctypes.c_void_p]
+    lib.spectral_last_error.argtypes = [ctypes.c_void_p]
+    lib.spectral_last_error.restype = ctypes.c_char_p
+    lib.spectral_default_options.argtypes = [ctypes.POINTER(SpectralOptions)]
+    for fn in (lib.spectral_solve_batch,):
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                       ctypes.POINTER(SpectralInputs), ctypes.POINTER(SpectralOptions), ctypes.POINTER(SpectralOutputs)]
+    lib.spectral_solve_batch_device.argtypes = lib.spectral_solve_batch.argtypes + [ctypes.c_void_p]
+    lib.spectral_argmin_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.spectral_launch_count.argtypes = [ctypes.c_void_p]
+    lib.spectral_launch_count.restype = ctypes.c_longlong
+    lib.spectral_measure_fp64_peak.argtypes = [ctypes.c_void_p, _dp]
+    lib.spectral_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.spectral_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    _lib = lib
+    return lib
+
+
+def default_options(**overrides) -> SpectralOptions:
+    o = SpectralOptions()
+    load_library().spectral_default_options(ctypes.byref(o))
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError("unknown option %r" % k)
+        setattr(o, k, v)
+    return o
+
+
+@dataclass
+class BatchResult:
+    K: np.ndarray        # [B] segment counts
+    segs: np.ndarray     # [B, k_max] CUBE_DTYPE, the selected corridor sequence (new_corridor)
+    ctrl: np.ndarray     # [B, 12*k_max] control points, s-axis [0,6K) then l-axis [6K,12K)
+    obj: np.ndarray      # [B] QP objective
+    a_cost: np.ndarray   # [B] wrapper cost (1e11 on failure)
+    status: np.ndarray   # [B]
+    iters: np.ndarray    # [B] ADMM iterations
+    flags: np.ndarray    # [B]
+    npts: np.ndarray     # [B]
+    samples: Optional[np.ndarray] = None  # [B, samples_cap, 6]
+    lu: Optional[np.ndarray] = None       # [B, 2, k_max, 21, 2]
+
+    def ok(self) -> np.ndarray:
+        return self.status <= SOLVED_INACCURATE
+
+    def verified(self) -> np.ndarray:
+        return self.ok() & ((self.flags & FLAG_VERIFIED) == FLAG_VERIFIED)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+class SpectralPlanner:
+    """One handle per GPU (spectral_create / spectral_destroy)."""
+
+    def __init__(self, device: int = 0, max_batch: int = 1024, n_max: int = 128, r_max: int = 8, k_max: int = 32):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self.device, self.max_batch, self.n_max, self.r_max, self.k_max = device, max_batch, n_max, r_max, k_max
+        rc = self._lib.spectral_create(device, max_batch, n_max, r_max, k_max, ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._lib.spectral_last_error(self._h).decode() if self._h else "no CUDA device"
+            self._h = ctypes.c_void_p()
+            raise RuntimeError("spectral_create failed (rc=%d): %s -- libspectral has no CPU path" % (rc, msg))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.spectral_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("libspectral error %d: %s" % (rc, self._lib.spectral_last_error(self._h).decode()))
+
+    # ---- end-to-end path: host (numpy) buffers, H2D + kernels + D2H inside the call
+    def solve(self, variant, batch: ScenarioBatch, weights: Sequence[float], options: Optional[SpectralOptions] = None,
+              samples_cap: int = 0, want_lu: bool = False) -> BatchResult:
+        B = batch.batch
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+        if w.shape not in ((10,), (B, 10)):
+            raise ValueError("weights must have shape (10,) or (B, 10)")
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in batch.arrays()]
+        inp = SpectralInputs(*[_d(a) for a in arrs], _d(w), 0 if w.ndim == 1 else 1)
+        km = self.k_max
+        res = BatchResult(np.zeros(B, np.int32), np.zeros((B, km), CUBE_DTYPE), np.zeros((B, 12 * km)), np.zeros(B),
+                          np.zeros(B), np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32),
+                          np.zeros(B, np.int32),
+                          np.zeros((B, samples_cap, 6)) if samples_cap > 0 else None,
+                          np.zeros((B, 2, km, 21, 2)) if want_lu else None)
+        out = SpectralOutputs(_i(res.K), res.segs.ctypes.data_as(ctypes.c_void_p), _d(res.ctrl), _d(res.obj),
+                              _d(res.a_cost), _i(res.status), _i(res.iters), _i(res.flags), _i(res.npts),
+                              _d(res.samples), samples_cap, _d(res.lu))
+        self._check(self._lib.spectral_solve_batch(self._h, VARIANT_ID[variant], B, batch.n_knots, batch.n_regions,
+                                                   float(batch.delta_t), ctypes.byref(inp),
+                                                   ctypes.byref(options) if options is not None else None,
+                                                   ctypes.byref(out)))
+        return res
+
+    # ---- resident path: torch CUDA tensors (float64 / int32), enqueued on the current stream
+    def solve_device(self, variant, n_knots: int, n_regions: int, delta_t: float, inputs: dict, outputs: dict,
+                     options: Optional[SpectralOptions] = None, stream: Optional[int] = None):
+        """inputs: s_bounds,l_bounds,ds_bounds,dl_bounds,s_ref,l_ref,init,scalars,weights (CUDA float64 tensors);
+        outputs: K,segs(uint8 [B,k_max*112]),ctrl,obj,a_cost,status,iters,flags,npts (CUDA tensors)."""
+        import torch
+        B = int(inputs["s_ref"].shape[0])
+        ptr = lambda t: ctypes.cast(ctypes.c_void_p(t.data_ptr()), _dp) if t is not None else None  # noqa: E731
+        iptr = lambda t: ctypes.cast(ctypes.c_void_p(t.data_ptr()), _ip) if t is not None else None  # noqa: E731
+        w = inputs["weights"]
+        inp = SpectralInputs(*[ptr(inputs[k]) for k in ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref",
+                                                        "l_ref", "init", "scalars")], ptr(w), 0 if w.dim() == 1 else 1)
+        g = outputs.get
+        out = SpectralOutputs(iptr(outputs["K"]), ctypes.c_void_p(outputs["segs"].data_ptr()), ptr(outputs["ctrl"]),
+                              ptr(g("obj")), ptr(g("a_cost")), iptr(outputs["status"]), iptr(g("iters")),
+                              iptr(g("flags")), iptr(g("npts")), ptr(g("samples")),
+                              int(g("samples").shape[1]) if g("samples") is not None else 0, ptr(g("lu")))
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self._check(self._lib.spectral_solve_batch_device(self._h, VARIANT_ID[variant], B, n_knots, n_regions,
+                                                          float(delta_t), ctypes.byref(inp),
+                                                          ctypes.byref(options) if options is not None else None,
+                                                          ctypes.byref(out), ctypes.c_void_p(stream)))
+
+    def alloc_device_outputs(self, B: int, samples_cap: int = 0):
+        import torch
+        dev = torch.device("cuda", self.device)
+        o = dict(K=torch.zeros(B, dtype=torch.int32, device=dev),
+                 segs=torch.zeros(B, self.k_max * 112, dtype=torch.uint8, device=dev),
+                 ctrl=torch.zeros(B, 12 * self.k_max, dtype=torch.float64, device=dev),
+                 obj=torch.zeros(B, dtype=torch.float64, device=dev),
+                 a_cost=torch.zeros(B, dtype=torch.float64, device=dev),
+                 status=torch.zeros(B, dtype=torch.int32, device=dev),
+                 iters=torch.zeros(B, dtype=torch.int32, device=dev),
+                 flags=torch.zeros(B, dtype=torch.int32, device=dev),
+                 npts=torch.zeros(B, dtype=torch.int32, device=dev))
+        if samples_cap:
+            o["samples"] = torch.zeros(B, samples_cap, 6, dtype=torch.float64, device=dev)
+        return o
+
+    def argmin_device(self, a_cost, index_offset: int, out_cost, out_index, stream: Optional[int] = None):
+        """(min cost, lowest index) of a CUDA float64 tensor -> out_cost (float64[1]), out_index (int64[1])."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self._check(self._lib.spectral_argmin_device(self._h, int(a_cost.numel()), ctypes.c_void_p(a_cost.data_ptr()),
+                                                     int(index_offset), ctypes.c_void_p(out_cost.data_ptr()),
+                                                     ctypes.c_void_p(out_index.data_ptr()), ctypes.c_void_p(stream)))
+
+    def launch_count(self) -> int:
+        return int(self._lib.spectral_launch_count(self._h))
+
+    def measure_fp64_peak(self) -> float:
+        v = ctypes.c_double()
+        self._check(self._lib.spectral_measure_fp64_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    def set_timing(self, on: bool):
+        self._check(self._lib.spectral_set_timing(self._h, 1 if on else 0))
+
+    def get_timing(self) -> dict:
+        ms = (ctypes.c_float * NUM_KERNELS)()
+        self._check(self._lib.spectral_get_timing(self._h, ms))
+        return {k: float(ms[i]) for i, k in enumerate(KERNEL_NAMES)}
+
+
+# ------------------------------------------------------------------ the reference's plugin surface
+_plugins = {}
+
+
+def _plugin(variant: str) -> ctypes.CDLL:
+    """Our libtrp.so / libcub.so (trp_wrapper.py:45-54: CDLL + argtypes + restype)."""
+    if variant not in _plugins:
+        path = lib_path("lib%s.so" % variant)
+        if not os.path.exists(path):
+            raise RuntimeError(path + " is missing (build with `make -C spectral_b200/csrc`)")
+        cdll = ctypes.CDLL(path)
+        cdll.find_traj.argtypes = (ctypes.POINTER(Params),)
+        cdll.find_traj.restype = ctypes.c_double
+        _plugins[variant] = cdll
+    return _plugins[variant]
+
+
+def _run_btrapz(params: Params, variant: str = "trp") -> float:
+    """`_run_btrapz = cdll.find_traj` of trp_wrapper.py:49: returns a_cost or 100000000000."""
+    return float(_plugin(variant).find_traj(ctypes.byref(params)))
+
+
+def find_traj(weights_file: Optional[str] = None, variant: str = "trp", iteration: int = 3) -> bool:
+    """trp_wrapper.py:99-121: read the tab-separated 10 weights, run find_traj, False iff it failed."""
+    if weights_file is None:
+        weights_file = os.path.join(os.environ.get("SPECTRAL_IO_DIR", "/home/srujan_d/RISS/code/btrapz/src"),
+                                    "weights.txt")
+    with open(weights_file) as f:
+        vals = [float(v) for v in f.readlines()[0].split("\t")[:10]]
+    return _run_btrapz(Params(*vals, iteration), variant) != FAIL_COST
+
+
+def run_btrapz(trial, variant: str = "trp") -> float:
+    """trp_wrapper.py:56-97: the Optuna objective -- 10 weights suggested in [0, 50], iteration = 1."""
+    names = ("s_acc_weight", "s_jerk_weight", "l_acc_weight", "l_jerk_weight", "weight_s_ref", "weight_ds_ref",
+             "weight_l_ref", "weight_dl_ref", "weight_end_s", "weight_end_l")
+    vals = [trial.suggest_float(n, 0, 50) for n in names]
+    return _run_btrapz(Params(*vals, 1), variant)

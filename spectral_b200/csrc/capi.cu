@@ -1,0 +1,456 @@
+// spectral_b200/csrc/capi.cu -- libspectral.so: the C-ABI of include/spectral.h and the __global__
+// wrappers of the QP-side kernels (tables, classify, qp<LPA>, finalize, argmin, fp64 peak probe).
+// The corridor kernel lives in corridor.cu (built with --fmad=false, see corridor.cuh).
+// There is no CPU path in this library: every entry point needs a CUDA device and reports
+// SPECTRAL_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "corridor.cuh"
+#include "finalize.cuh"
+#include "qp.cuh"
+#include "tables.cuh"
+
+extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
+extern "C" int spectral_corridor_prepare(int N, int R);                           // corridor.cu
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_tables(const double *weights, double *mqm, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * W) mqm_body(weights, mqm, i >> 1, i & 1);
+}
+
+__global__ void k_classify(const int *cstatus, const int *K, int B, int *lists, int *counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || cstatus[b] != 0) return;
+  const int cls = lane_class(K[b]);
+  const int slot = atomicAdd(&counts[cls], 1);
+  lists[(size_t)cls * B + slot] = b;
+}
+
+// classification that keeps scenario order (one CTA, used for small batches so runs are reproducible
+// lane-for-lane; the atomic version above is used for large ones)
+__global__ void k_classify_ordered(const int *cstatus, const int *K, int B, int *lists, int *counts) {
+  __shared__ int base[3];
+  __shared__ int wsum[3][32];
+  if (threadIdx.x < 3) base[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int start = 0; start < B; start += blockDim.x) {
+    const int b = start + threadIdx.x;
+    int cls = -1;
+    if (b < B && cstatus[b] == 0) cls = lane_class(K[b]);
+    int pos[3];
+    for (int c = 0; c < 3; c++) {
+      const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+      pos[c] = __popc(m & ((1u << lane) - 1));
+      if (lane == 0) wsum[c][warp] = __popc(m);
+    }
+    __syncthreads();
+    if (cls >= 0) {
+      int off = base[cls];
+      for (int w = 0; w < warp; w++) off += wsum[cls][w];
+      lists[(size_t)cls * B + off + pos[cls]] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      int tot = 0;
+      for (int w = 0; w < nw; w++) tot += wsum[threadIdx.x][w];
+      base[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) counts[threadIdx.x] = base[threadIdx.x];
+}
+
+template <int LPA, int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
+  extern __shared__ double qp_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  qp_warp_body<LPA>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
+}
+
+__global__ void k_finalize(const FinalArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.B) finalize_body(a, b);
+}
+
+// K6: (min cost, lowest index) -- two-stage, last block finishes (ticket)
+struct ArgminPair { double cost; long long idx; };
+__device__ __forceinline__ ArgminPair argmin_better(ArgminPair a, ArgminPair b) {
+  return (b.cost < a.cost || (b.cost == a.cost && b.idx < a.idx)) ? b : a;
+}
+__global__ void k_argmin(const double *cost, int B, long long offset, ArgminPair *partial, unsigned *ticket,
+                         double *out_cost, long long *out_idx) {
+  __shared__ ArgminPair sh[32];
+  __shared__ bool is_last;
+  ArgminPair best{1.0e300, 0x7fffffffffffffffLL};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+    best = argmin_better(best, ArgminPair{cost[i], offset + i});
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int m = 16; m > 0; m >>= 1) {
+    ArgminPair o{__shfl_xor_sync(0xffffffffu, best.cost, m), __shfl_xor_sync(0xffffffffu, best.idx, m)};
+    best = argmin_better(best, o);
+  }
+  if (lane == 0) sh[warp] = best;
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < nw ? sh[lane] : ArgminPair{1.0e300, 0x7fffffffffffffffLL};
+    for (int m = 16; m > 0; m >>= 1) {
+      ArgminPair o{__shfl_xor_sync(0xffffffffu, best.cost, m), __shfl_xor_sync(0xffffffffu, best.idx, m)};
+      best = argmin_better(best, o);
+    }
+    if (lane == 0) {
+      partial[blockIdx.x] = best;
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    best = ArgminPair{1.0e300, 0x7fffffffffffffffLL};
+    for (int i = lane; i < (int)gridDim.x; i += 32) best = argmin_better(best, partial[i]);
+    for (int m = 16; m > 0; m >>= 1) {
+      ArgminPair o{__shfl_xor_sync(0xffffffffu, best.cost, m), __shfl_xor_sync(0xffffffffu, best.idx, m)};
+      best = argmin_better(best, o);
+    }
+    if (lane == 0) { *out_cost = best.cost; *out_idx = best.idx; *ticket = 0; }
+  }
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------ handle
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct spectral_handle {
+  int device = 0, max_batch = 0, n_max = 0, r_max = 0, k_max = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;  // used by the host-buffer entry point
+  std::string err;
+  long long launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[SPECTRAL_NUM_KERNELS + 1] = {};
+  float ms[SPECTRAL_NUM_KERNELS] = {};
+  // intermediates
+  int *cstatus = nullptr, *lists = nullptr, *counts = nullptr, *axis_status = nullptr, *axis_iters = nullptr,
+      *axis_polished = nullptr;
+  double *axis_obj = nullptr, *mqm = nullptr;
+  ArgminPair *partial = nullptr;
+  unsigned *ticket = nullptr;
+  // device mirrors for the host-buffer entry point
+  double *d_in[9] = {};
+  size_t d_in_bytes[9] = {};
+  int *d_K = nullptr, *d_status = nullptr, *d_iters = nullptr, *d_flags = nullptr, *d_npts = nullptr;
+  SpectralCube *d_segs = nullptr;
+  double *d_ctrl = nullptr, *d_obj = nullptr, *d_cost = nullptr, *d_samples = nullptr, *d_lu = nullptr;
+  size_t d_samples_bytes = 0, d_lu_bytes = 0;
+  bool qp_attr_set = false;
+};
+
+static int fail(spectral_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, SPECTRAL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+extern "C" void spectral_default_options(SpectralOptions *o) {
+  o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
+  o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
+  o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
+}
+
+extern "C" const char *spectral_last_error(const spectral_handle_t *h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" long long spectral_launch_count(const spectral_handle_t *h) { return h ? h->launches : 0; }
+
+extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, int k_max, spectral_handle_t **out) {
+  if (!out) return SPECTRAL_ERR_INVALID;
+  *out = nullptr;
+  if (max_batch <= 0 || n_max < 3 || n_max > SP_MAX_KNOTS || r_max < 1 || r_max > SP_MAX_REGIONS || k_max < 1 || k_max > 32)
+    return SPECTRAL_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+    fprintf(stderr, "libspectral: no CUDA device (this library has no CPU path)\n");
+    return SPECTRAL_ERR_CUDA;
+  }
+  spectral_handle *h = new spectral_handle();
+  h->device = device; h->max_batch = max_batch; h->n_max = n_max; h->r_max = r_max; h->k_max = k_max;
+  *out = h;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t B = (size_t)max_batch;
+  CK(cudaMalloc(&h->cstatus, B * 4));
+  CK(cudaMalloc(&h->lists, 3 * B * 4));
+  CK(cudaMalloc(&h->counts, 16));
+  CK(cudaMalloc(&h->axis_status, 2 * B * 4));
+  CK(cudaMalloc(&h->axis_iters, 2 * B * 4));
+  CK(cudaMalloc(&h->axis_polished, 2 * B * 4));
+  CK(cudaMalloc(&h->axis_obj, 2 * B * 8));
+  CK(cudaMalloc(&h->mqm, B * 2 * 84 * 8));
+  CK(cudaMalloc(&h->partial, 1024 * sizeof(ArgminPair)));
+  CK(cudaMalloc(&h->ticket, 4));
+  CK(cudaMemset(h->ticket, 0, 4));
+  for (auto &e : h->ev) CK(cudaEventCreate(&e));
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_destroy(spectral_handle_t *h) {
+  if (!h) return SPECTRAL_ERR_INVALID;
+  cudaSetDevice(h->device);
+  void *bufs[] = {h->cstatus, h->lists, h->counts, h->axis_status, h->axis_iters, h->axis_polished, h->axis_obj, h->mqm,
+                  h->partial, h->ticket, h->d_K, h->d_status, h->d_iters, h->d_flags, h->d_npts, h->d_segs, h->d_ctrl,
+                  h->d_obj, h->d_cost, h->d_samples, h->d_lu};
+  for (void *p : bufs) if (p) cudaFree(p);
+  for (auto p : h->d_in) if (p) cudaFree(p);
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_set_timing(spectral_handle_t *h, int enabled) {
+  if (!h) return SPECTRAL_ERR_INVALID;
+  h->timing = enabled != 0;
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS]) {
+  if (!h) return SPECTRAL_ERR_INVALID;
+  memcpy(ms, h->ms, sizeof(h->ms));
+  return SPECTRAL_SUCCESS;
+}
+
+template <int LPA, int WPB>
+static cudaError_t launch_qp(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
+  constexpr int G = 32 / LPA;
+  const size_t smem = (size_t)WPB * QP_SMEM_PER_WARP;
+  cudaError_t e = cudaFuncSetAttribute(k_qp<LPA, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int warps = (2 * B + G - 1) / G;
+  const int blocks = (warps + WPB - 1) / WPB;
+  k_qp<LPA, WPB><<<blocks, 32 * WPB, smem, st>>>(qa);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                           const SpectralInputs *in, const SpectralOptions *opt_in,
+                                           SpectralOutputs *out, void *cuda_stream) {
+  if (!h || !in || !out) return SPECTRAL_ERR_INVALID;
+  if (B <= 0 || B > h->max_batch || N < 3 || N > h->n_max || R < 1 || R > h->r_max)
+    return fail(h, SPECTRAL_ERR_CAPACITY, "batch shape exceeds the handle's capacity");
+  if (variant != SPECTRAL_TRP && variant != SPECTRAL_CUB) return fail(h, SPECTRAL_ERR_INVALID, "variant");
+  if (!out->K || !out->status || !out->segs || !out->ctrl) return fail(h, SPECTRAL_ERR_INVALID, "K/status/segs/ctrl outputs are required");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  SpectralOptions opt;
+  if (opt_in) opt = *opt_in; else spectral_default_options(&opt);
+  const bool tm = h->timing;
+  int evi = 0;
+  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+
+  // K3a: weight tables
+  const int W = in->weights_stride ? B : 1;
+  k_tables<<<(2 * W + 127) / 128, 128, 0, st>>>(in->weights, h->mqm, W);
+  h->launches++;
+  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+
+  // K1 + K2: corridors
+  CorridorArgs ca{B, N, R, variant, h->k_max, delta_t, in->s_bounds, in->l_bounds, in->s_ref, in->l_ref, out->segs, out->K, h->cstatus};
+  if (spectral_corridor_prepare(N, R) != 0) return fail(h, SPECTRAL_ERR_CUDA, "corridor kernel: shared memory opt-in failed");
+  spectral_launch_corridor(ca, st);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+
+  // classification by segment count -> lane class lists
+  CK(cudaMemsetAsync(h->counts, 0, 16, st));
+  if (B <= 4096) k_classify_ordered<<<1, 1024, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
+  else k_classify<<<(B + 255) / 256, 256, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
+  h->launches++;
+  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+
+  // K3 + K4b: QP per lane class
+  QpArgs qa;
+  qa.N = N; qa.k_max = h->k_max; qa.variant = variant; qa.delta = delta_t;
+  qa.ds_bounds = in->ds_bounds; qa.dl_bounds = in->dl_bounds; qa.s_ref = in->s_ref; qa.l_ref = in->l_ref;
+  qa.init = in->init; qa.scalars = in->scalars; qa.weights = in->weights; qa.wstride = in->weights_stride;
+  qa.mqm = h->mqm; qa.segs = out->segs; qa.K = out->K;
+  qa.opt.max_iter = opt.max_iter; qa.opt.scaling = opt.scaling; qa.opt.check_every = opt.check_termination;
+  qa.opt.adapt_every = opt.adaptive_rho_interval; qa.opt.polish = opt.polish; qa.opt.polish_refine = opt.polish_refine_iter;
+  qa.opt.eps_abs = opt.eps_abs; qa.opt.eps_rel = opt.eps_rel; qa.opt.eps_pinf = opt.eps_prim_inf; qa.opt.rho0 = opt.rho;
+  qa.opt.sigma = opt.sigma; qa.opt.alpha = opt.alpha; qa.opt.adapt_tol = opt.adaptive_rho_tolerance;
+  qa.opt.polish_delta = opt.polish_delta; qa.opt.polish_rounds = opt.polish_rounds;
+  qa.ctrl = out->ctrl; qa.axis_status = h->axis_status; qa.axis_iters = h->axis_iters; qa.axis_polished = h->axis_polished;
+  qa.axis_obj = h->axis_obj; qa.lu = out->lu;
+  qa.list = h->lists; qa.count = h->counts + 0;
+  CK((launch_qp<8, 2>(h, qa, B, st)));
+  if (h->k_max > 8) {
+    qa.list = h->lists + (size_t)B; qa.count = h->counts + 1;
+    CK((launch_qp<16, 2>(h, qa, B, st)));
+  }
+  if (h->k_max > 16) {
+    qa.list = h->lists + 2 * (size_t)B; qa.count = h->counts + 2;
+    CK((launch_qp<32, 2>(h, qa, B, st)));
+  }
+  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+
+  // K5: sampling + cost + status merge
+  FinalArgs fa;
+  fa.B = B; fa.N = N; fa.k_max = h->k_max; fa.variant = variant; fa.delta = delta_t; fa.s_ref = in->s_ref; fa.l_ref = in->l_ref;
+  fa.init = in->init; fa.weights = in->weights; fa.wstride = in->weights_stride; fa.segs = out->segs; fa.K = out->K;
+  fa.cstatus = h->cstatus; fa.axis_status = h->axis_status; fa.axis_iters = h->axis_iters; fa.axis_polished = h->axis_polished;
+  fa.axis_obj = h->axis_obj; fa.ctrl = out->ctrl; fa.obj = out->obj; fa.a_cost = out->a_cost; fa.samples = out->samples;
+  fa.status = out->status; fa.iters = out->iters; fa.flags = out->flags; fa.npts = out->npts; fa.samples_cap = out->samples_cap;
+  k_finalize<<<(B + 127) / 128, 128, 0, st>>>(fa);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (tm) {
+    CK(cudaEventRecord(h->ev[evi++], st));
+    CK(cudaEventSynchronize(h->ev[evi - 1]));
+    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&h->ms[i], h->ev[i], h->ev[i + 1]));
+  }
+  return SPECTRAL_SUCCESS;
+}
+
+static int dev_alloc(spectral_handle *h, void **p, size_t bytes) {
+  CK(cudaMalloc(p, bytes));
+  return SPECTRAL_SUCCESS;
+}
+
+template <typename T>
+static int ensure(spectral_handle *h, T **p, size_t *cur, size_t need) {
+  if (*cur >= need && *p) return SPECTRAL_SUCCESS;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  CK(cudaMalloc((void **)p, need));
+  *cur = need;
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_solve_batch(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                    const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
+  if (!h || !hin || !hout) return SPECTRAL_ERR_INVALID;
+  if (B <= 0 || B > h->max_batch) return fail(h, SPECTRAL_ERR_CAPACITY, "batch exceeds max_batch");
+  if (!hout->K || !hout->status) return fail(h, SPECTRAL_ERR_INVALID, "K and status outputs are required");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t b = (size_t)B, n = (size_t)N, r = (size_t)R, km = (size_t)h->k_max;
+  const size_t in_bytes[9] = {b * r * n * 16, b * r * n * 16, b * n * 16, b * n * 16, b * n * 8, b * n * 8, b * 48, b * 80,
+                              (hin->weights_stride ? b : 1) * 80};
+  const double *src[9] = {hin->s_bounds, hin->l_bounds, hin->ds_bounds, hin->dl_bounds, hin->s_ref, hin->l_ref, hin->init,
+                          hin->scalars, hin->weights};
+  for (int i = 0; i < 9; i++) {
+    if (!src[i]) return fail(h, SPECTRAL_ERR_INVALID, "null input");
+    int rc = ensure(h, &h->d_in[i], &h->d_in_bytes[i], in_bytes[i]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_in[i], src[i], in_bytes[i], cudaMemcpyHostToDevice, st));
+  }
+  {
+    const size_t mb = (size_t)h->max_batch;
+    int rc = 0;
+    if (!h->d_K) rc |= dev_alloc(h, (void **)&h->d_K, mb * 4);
+    if (!h->d_status) rc |= dev_alloc(h, (void **)&h->d_status, mb * 4);
+    if (!h->d_iters) rc |= dev_alloc(h, (void **)&h->d_iters, mb * 4);
+    if (!h->d_flags) rc |= dev_alloc(h, (void **)&h->d_flags, mb * 4);
+    if (!h->d_npts) rc |= dev_alloc(h, (void **)&h->d_npts, mb * 4);
+    if (!h->d_segs) rc |= dev_alloc(h, (void **)&h->d_segs, mb * km * sizeof(SpectralCube));
+    if (!h->d_ctrl) rc |= dev_alloc(h, (void **)&h->d_ctrl, mb * 12 * km * 8);
+    if (!h->d_obj) rc |= dev_alloc(h, (void **)&h->d_obj, mb * 8);
+    if (!h->d_cost) rc |= dev_alloc(h, (void **)&h->d_cost, mb * 8);
+    if (rc) return SPECTRAL_ERR_CUDA;
+  }
+  if (hout->samples) { int rc = ensure(h, &h->d_samples, &h->d_samples_bytes, b * (size_t)hout->samples_cap * 48); if (rc) return rc; }
+  if (hout->lu) { int rc = ensure(h, &h->d_lu, &h->d_lu_bytes, b * 2 * km * QP_ROWS * 16); if (rc) return rc; }
+  SpectralInputs din = *hin;
+  din.s_bounds = h->d_in[0]; din.l_bounds = h->d_in[1]; din.ds_bounds = h->d_in[2]; din.dl_bounds = h->d_in[3];
+  din.s_ref = h->d_in[4]; din.l_ref = h->d_in[5]; din.init = h->d_in[6]; din.scalars = h->d_in[7]; din.weights = h->d_in[8];
+  SpectralOutputs dout;
+  memset(&dout, 0, sizeof(dout));
+  dout.K = h->d_K; dout.segs = h->d_segs; dout.ctrl = h->d_ctrl; dout.obj = h->d_obj; dout.a_cost = h->d_cost;
+  dout.status = h->d_status; dout.iters = h->d_iters; dout.flags = h->d_flags; dout.npts = h->d_npts;
+  dout.samples = hout->samples ? h->d_samples : nullptr; dout.samples_cap = hout->samples_cap;
+  dout.lu = hout->lu ? h->d_lu : nullptr;
+  if (hout->lu) CK(cudaMemsetAsync(h->d_lu, 0, b * 2 * km * QP_ROWS * 16, st));
+  CK(cudaMemsetAsync(h->d_ctrl, 0, b * 12 * km * 8, st));
+  CK(cudaMemsetAsync(h->d_segs, 0, b * km * sizeof(SpectralCube), st));
+  if (hout->samples) CK(cudaMemsetAsync(h->d_samples, 0, b * (size_t)hout->samples_cap * 48, st));
+  int rc = spectral_solve_batch_device(h, variant, B, N, R, delta_t, &din, opt, &dout, st);
+  if (rc) return rc;
+#define D2H(dst, srcp, bytes) do { if (dst) CK(cudaMemcpyAsync((dst), (srcp), (bytes), cudaMemcpyDeviceToHost, st)); } while (0)
+  D2H(hout->K, h->d_K, b * 4); D2H(hout->status, h->d_status, b * 4); D2H(hout->iters, h->d_iters, b * 4);
+  D2H(hout->flags, h->d_flags, b * 4); D2H(hout->npts, h->d_npts, b * 4);
+  D2H(hout->segs, h->d_segs, b * km * sizeof(SpectralCube)); D2H(hout->ctrl, h->d_ctrl, b * 12 * km * 8);
+  D2H(hout->obj, h->d_obj, b * 8); D2H(hout->a_cost, h->d_cost, b * 8);
+  D2H(hout->samples, h->d_samples, b * (size_t)hout->samples_cap * 48);
+  D2H(hout->lu, h->d_lu, b * 2 * km * QP_ROWS * 16);
+#undef D2H
+  CK(cudaStreamSynchronize(st));
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,
+                                      double *out_cost_dev, long long *out_index_dev, void *cuda_stream) {
+  if (!h || B <= 0 || !a_cost_dev || !out_cost_dev || !out_index_dev) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int blocks = (B + 255) / 256;
+  const int cap = h->sm_count * 4 < 1024 ? h->sm_count * 4 : 1024;
+  if (blocks > cap) blocks = cap;
+  k_argmin<<<blocks, 256, 0, st>>>(a_cost_dev, B, index_offset, h->partial, h->ticket, out_cost_dev, out_index_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_measure_fp64_peak(spectral_handle_t *h, double *tflops) {
+  if (!h || !tflops) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 15;
+  double *buf = nullptr;
+  CK(cudaMalloc(&buf, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(buf, iters);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return SPECTRAL_SUCCESS;
+}

@@ -1,0 +1,118 @@
+"""Synthetic scenario batches of the shapes named in BASELINE.json.
+
+* ``load_fixture``            the reference's input fixtures (src/c*.txt, bounds.txt), shipped parsed
+                              in ``spectral_b200/data/fixtures.npz`` (written by oracle/gen_golden.py).
+* ``perturbed_obstacles``     config 2 / 5: B obstacle-perturbed copies of one base scenario: per region
+                              the obstacle ramp of the s-bounds is shifted by dk in {-5..5} knots and
+                              ds = round(U(-2,2), 2) m, the lane edges by round(U(-0.3,0.3), 2) m.
+* ``mixed_batch``             config 4: base drawn from the feasible fixtures, extra breakpoints.
+Random numbers come from a counter-based generator (Philox) keyed by the seed, drawn in scenario
+order, so scenario b is the same whatever the batch size; scenario 0 is the unperturbed base.
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import numpy as np
+
+from .wire import Scenario, ScenarioBatch
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "fixtures.npz")
+FIXTURES = ("c1", "c2", "c3", "c4", "c4_2", "c5", "c6", "c7", "c7_7", "c7_10", "c_road_s1", "c_road_s1_2",
+            "c_road_s1_3", "bounds")
+FEASIBLE = ("c1", "c2", "c3", "c4", "c4_2", "c5", "bounds")
+
+# src/weights.txt and the golden recipes
+WEIGHTS_FILE = (35.73, 41.61, 25.57, 41.59, 0.12, 10.04, 0.71, 14.3, 7.27, 32.13)
+GOLDEN_W_TRP = (35.73, 41.61, 25.57, 41.59, 0.12, 10.04, 0.0, 0.0, 7.27, 32.13)
+GOLDEN_W_CUB = (35.73, 41.61, 25.57, 41.59, 0.12, 10.04, 0.0, 0.0, 7.27, 0.0)
+
+_cache = None
+
+
+def load_fixture(name: str) -> Scenario:
+    global _cache
+    if _cache is None:
+        _cache = np.load(_DATA)
+    z = _cache
+    g = lambda k: z["%s/%s" % (name, k)]  # noqa: E731
+    init = g("init")
+    return Scenario(int(g("n_knots")), float(g("delta_t")), init[:3].copy(), init[3:].copy(), g("scalars").copy(),
+                    g("s_bounds").copy(), g("l_bounds").copy(), g("ds_bounds").copy(), g("dl_bounds").copy(),
+                    g("s_ref").copy(), g("l_ref").copy())
+
+
+def _mode(col: np.ndarray) -> float:
+    vals, counts = np.unique(col, return_counts=True)
+    return float(vals[np.argmax(counts)])
+
+
+def perturbed_obstacles(base: Scenario, B: int, seed: int = 20230531, first: int = 0, s_max: float = 50.0) -> ScenarioBatch:
+    """Scenarios [first, first+B) of the config-2 family built on `base` (vectorised over scenarios)."""
+    N, R = base.n_knots, base.n_regions
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    if first:
+        rng.bit_generator.advance(first * R)  # one Philox block (4 draws) per (scenario, region)
+    u = rng.random((B, R, 4))
+    dk = np.floor(u[..., 0] * 11).astype(np.int64) - 5
+    ds = np.round(u[..., 1] * 4.0 - 2.0, 2)
+    dl_lo = np.round(u[..., 2] * 0.6 - 0.3, 2)
+    dl_hi = np.round(u[..., 3] * 0.6 - 0.3, 2)
+    if first == 0:
+        dk[0], ds[0], dl_lo[0], dl_hi[0] = 0, 0.0, 0.0, 0.0
+    idx = np.arange(N)[None, None, :] - dk[..., None]          # source knot of each destination knot
+    valid = (idx >= 0) & (idx < N)
+    src = np.clip(idx, 0, N - 1)
+    s_out = np.empty((B, R, N, 2))
+    for side in (0, 1):
+        col = base.s_bounds[:, :, side]                          # [R, N]
+        default = np.array([_mode(col[r]) for r in range(R)])    # the region's free-road value (0 or 50)
+        is_obst = col != default[:, None]
+        r_idx = np.arange(R)[None, :, None]
+        moved = np.clip(np.round(col[r_idx, src] + ds[..., None], 2), 0.0, s_max)
+        take = valid & is_obst[r_idx, src]
+        s_out[..., side] = np.where(take, moved, default[None, :, None])
+    s_out[..., 1] = np.maximum(s_out[..., 1], s_out[..., 0])     # keep lo <= hi
+    l_out = np.broadcast_to(base.l_bounds, (B, R, N, 2)).copy()
+    l_out[..., 0] = np.round(l_out[..., 0] + dl_lo[..., None], 2)
+    l_out[..., 1] = np.round(l_out[..., 1] + dl_hi[..., None], 2)
+    l_out[..., 1] = np.maximum(l_out[..., 1], l_out[..., 0])
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))  # noqa: E731
+    return ScenarioBatch(N, R, base.delta_t, np.ascontiguousarray(s_out), np.ascontiguousarray(l_out),
+                         rep(base.ds_bounds), rep(base.dl_bounds), rep(base.s_ref), rep(base.l_ref),
+                         rep(np.concatenate([base.init_s, base.init_l])), rep(base.scalars))
+
+
+def config2(B: int = 1024, first: int = 0) -> ScenarioBatch:
+    """BASELINE.json configs[1]: scenario_1 (c1.txt), cuboid variant, obstacle-perturbed copies."""
+    return perturbed_obstacles(load_fixture("c1"), B, seed=20230531, first=first)
+
+
+def with_extra_breaks(batch: ScenarioBatch, seed: int, max_breaks: int = 4) -> ScenarioBatch:
+    """config 4 ingredient: random extra slope breaks (a 0.5 m step in the upper s-bound from a random
+    knot on) so that the segment count K varies between scenarios."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    B, R, N = batch.batch, batch.n_regions, batch.n_knots
+    s = batch.s_bounds.copy()
+    nb = rng.integers(0, max_breaks + 1, size=B)
+    at = rng.integers(3, N - 3, size=(B, max_breaks))
+    step = np.round(rng.random((B, max_breaks)) * 1.0 + 0.5, 2)
+    knots = np.arange(N)[None, :]
+    for j in range(max_breaks):
+        on = (nb > j)[:, None] & (knots >= at[:, j:j + 1])
+        s[:, 0, :, 1] = np.where(on, np.maximum(s[:, 0, :, 1] - step[:, j:j + 1], s[:, 0, :, 0]), s[:, 0, :, 1])
+    return ScenarioBatch(N, R, batch.delta_t, s, batch.l_bounds, batch.ds_bounds, batch.dl_bounds, batch.s_ref,
+                         batch.l_ref, batch.init, batch.scalars)
+
+
+def mixed_batches(B: int, seed: int = 20230602, bases: Sequence[str] = ("c1", "c3", "bounds", "c2", "c4_2")):
+    """config 4: heterogeneous corridor sequences.  Returns a list of (variant, ScenarioBatch): the C-ABI takes
+    one (N, R, variant) per call, so a mixed sweep is a handful of calls on one stream."""
+    out = []
+    per = max(1, B // (2 * len(bases)))
+    for i, name in enumerate(bases):
+        for variant in ("trp", "cub"):
+            b = perturbed_obstacles(load_fixture(name), per, seed=seed + 17 * i + (variant == "cub"))
+            out.append((variant, with_extra_breaks(b, seed + 1000 + i)))
+    return out

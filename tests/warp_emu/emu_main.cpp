@@ -1,0 +1,113 @@
+// tests/warp_emu/emu_main.cpp -- TEST INFRASTRUCTURE: runs the device "bodies" of
+// spectral_b200/csrc/{corridor,qp,finalize,tables}.cuh on the host, one warp = 32 pthreads in
+// lock step (see warp_emu.h).  Built by tests/warp_emu/Makefile into libwarp_emu.so and used by
+// tests/test_kernel_logic_emu.py to compare the kernels' logic with the CPU oracle where no GPU
+// exists.  Not part of the product.
+#define SPECTRAL_CPU_EMU 1
+#include "../../spectral_b200/csrc/common.cuh"
+#include "../../spectral_b200/csrc/corridor.cuh"
+#include "../../spectral_b200/csrc/qp.cuh"
+#include "../../spectral_b200/csrc/tables.cuh"
+#include "../../spectral_b200/csrc/finalize.cuh"
+
+#include <cstdlib>
+#include <functional>
+#include <thread>
+#include <vector>
+
+thread_local EmuWarp *emu_warp = nullptr;
+thread_local int emu_lane = 0;
+
+static void run_warps(int nwarps, const std::function<void(int, int, pthread_barrier_t *)> &fn) {
+  std::vector<EmuWarp> warps(nwarps);
+  pthread_barrier_t cta;
+  pthread_barrier_init(&cta, nullptr, 32 * nwarps);
+  for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
+  std::vector<std::thread> th;
+  for (int w = 0; w < nwarps; w++)
+    for (int l = 0; l < 32; l++)
+      th.emplace_back([&, w, l]() {
+        emu_warp = &warps[w];
+        emu_lane = l;
+        fn(w, l, &cta);
+      });
+  for (auto &t : th) t.join();
+  for (auto &w : warps) pthread_barrier_destroy(&w.bar);
+  pthread_barrier_destroy(&cta);
+}
+
+extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, const double *s_bounds,
+                               const double *l_bounds, const double *ds_bounds, const double *dl_bounds,
+                               const double *s_ref, const double *l_ref, const double *init,
+                               const double *scalars, const double *weights, int wstride, int k_max,
+                               const SpectralOptions *opt, int *K, SpectralCube *segs, double *ctrl,
+                               double *obj, double *a_cost, int *status, int *iters, int *flags, int *npts,
+                               double *samples, int samples_cap, double *lu) {
+  std::vector<int> cstatus(B, 0);
+  // ---- corridor kernel: one CTA per scenario, R warps
+  CorridorArgs ca{B, N, R, variant, k_max, delta, s_bounds, l_bounds, s_ref, l_ref, segs, K, cstatus.data()};
+  CorridorSmem L = corridor_smem_layout(N, R);
+  for (int b = 0; b < B; b++) {
+    std::vector<unsigned char> smem(L.total + 64);
+    unsigned char *base = smem.data();
+    base += (16 - ((uintptr_t)base & 15)) & 15;
+    run_warps(R, [&](int w, int l, pthread_barrier_t *cta) {
+      // every thread must reach the CTA barrier the same number of times: the body returns early
+      // only after its last sync_cta(), as on the device
+      corridor_cta_body(ca, b, w, l, base, [cta]() { pthread_barrier_wait(cta); });
+    });
+  }
+  // ---- tables
+  const int W = wstride ? B : 1;
+  std::vector<double> mqm((size_t)W * 2 * 84);
+  for (int w = 0; w < W; w++)
+    for (int ax = 0; ax < 2; ax++) mqm_body(weights, mqm.data(), w, ax);
+  // ---- classification
+  std::vector<int> list[3];
+  for (int b = 0; b < B; b++)
+    if (cstatus[b] == 0) list[lane_class(K[b])].push_back(b);
+  // ---- QP kernel per lane class
+  std::vector<int> axis_status(2 * B, QP_ST_MAXITER), axis_iters(2 * B, 0), axis_pol(2 * B, 0);
+  std::vector<double> axis_obj(2 * B, 0.0);
+  SpOptionsDev od;
+  od.max_iter = opt->max_iter; od.scaling = opt->scaling; od.check_every = opt->check_termination;
+  od.adapt_every = opt->adaptive_rho_interval; od.polish = opt->polish; od.polish_refine = opt->polish_refine_iter;
+  od.eps_abs = opt->eps_abs; od.eps_rel = opt->eps_rel; od.eps_pinf = opt->eps_prim_inf; od.rho0 = opt->rho;
+  od.sigma = opt->sigma; od.alpha = opt->alpha; od.adapt_tol = opt->adaptive_rho_tolerance; od.polish_delta = opt->polish_delta; od.polish_rounds = opt->polish_rounds;
+  for (int cls = 0; cls < 3; cls++) {
+    int cnt = (int)list[cls].size();
+    if (!cnt) continue;
+    QpArgs qa;
+    qa.N = N; qa.k_max = k_max; qa.variant = variant; qa.delta = delta;
+    qa.ds_bounds = ds_bounds; qa.dl_bounds = dl_bounds; qa.s_ref = s_ref; qa.l_ref = l_ref; qa.init = init;
+    qa.scalars = scalars; qa.weights = weights; qa.wstride = wstride; qa.mqm = mqm.data(); qa.segs = segs; qa.K = K;
+    qa.list = list[cls].data(); qa.count = &cnt; qa.opt = od; qa.ctrl = ctrl; qa.axis_status = axis_status.data();
+    qa.axis_iters = axis_iters.data(); qa.axis_polished = axis_pol.data(); qa.axis_obj = axis_obj.data(); qa.lu = lu;
+    const int lpa = cls == 0 ? 8 : (cls == 1 ? 16 : 32);
+    const int G = 32 / lpa;
+    const int nw = (2 * cnt + G - 1) / G;
+    for (int w = 0; w < nw; w++) {
+      std::vector<double> sm(QP_SM_DOUBLES_PER_LANE * 32);
+      run_warps(1, [&](int, int l, pthread_barrier_t *) {
+        if (lpa == 8) qp_warp_body<8>(qa, w, l, sm.data());
+        else if (lpa == 16) qp_warp_body<16>(qa, w, l, sm.data());
+        else qp_warp_body<32>(qa, w, l, sm.data());
+      });
+    }
+  }
+  // ---- finalize
+  FinalArgs fa;
+  fa.B = B; fa.N = N; fa.k_max = k_max; fa.variant = variant; fa.delta = delta; fa.s_ref = s_ref; fa.l_ref = l_ref;
+  fa.init = init; fa.weights = weights; fa.wstride = wstride; fa.segs = segs; fa.K = K; fa.cstatus = cstatus.data();
+  fa.axis_status = axis_status.data(); fa.axis_iters = axis_iters.data(); fa.axis_polished = axis_pol.data();
+  fa.axis_obj = axis_obj.data(); fa.ctrl = ctrl; fa.obj = obj; fa.a_cost = a_cost; fa.samples = samples;
+  fa.status = status; fa.iters = iters; fa.flags = flags; fa.npts = npts; fa.samples_cap = samples_cap;
+  for (int b = 0; b < B; b++) finalize_body(fa, b);
+  return 0;
+}
+
+extern "C" void emu_default_options(SpectralOptions *o) {
+  o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
+  o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
+  o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
+}

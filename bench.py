@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- corridor+QP trajectory solves/sec of the planning hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...    the reference's own CPU code on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- scenario_1 (c1.txt), CUBOID corridors (libcub.so
+path), a batch of 1024 obstacle-perturbed copies per step and per GPU (SURVEY.md 8d "Config 2", seed
+20230531).  One step = one pass of the whole hot path (corridor generation/split/selection, QP assembly,
+ADMM solve + polish, Bezier sampling, cost, local argmin) over one batch.  Weak scaling: every rank
+processes its own 1024-scenario shards (scenario ids rank*POOL*1024 ...), the only exchange is the final
+(cost, index) arg-min gather over NCCL.
+
+value : whole-job solves/s with the inputs already resident in HBM (CUDA events, max over ranks).
+        L2 hygiene: the step rotates through a pool of distinct batches whose inputs + outputs exceed the
+        126 MB L2 ("inputs larger than L2").
+e2e   : same metric through spectral_solve_batch() with HOST buffers (pinned), H2D + D2H inside the timed region.
+roofline      : the dominant kernel (k_qp, batched ADMM): algorithmic FP64 flops / its CUDA-event time vs the
+                FP64 FMA peak measured on this device by the library's probe kernel; plus `roofline_corridor`,
+                the HBM-bound corridor kernel, against MEASURED_PEAKS.json.
+cpu_baseline  : the reference's own sources (oracle/_ref, OSQP restated) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corridor+QP trajectory solves/sec"
+UNIT = "solves/s"
+BATCH = 1024
+SEED_NOTE = "config2: c1.txt base, cub, 1024 obstacle-perturbed copies/step/GPU, seed 20230531"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _cpu_reference(batch, weights, n_scen, threads):
+    """The reference's CPU implementation of the path on `n_scen` scenarios: oracle/_ref (the reference's own
+    sources + OSQP restatement) when present, else the plain-C port.  Returns (seconds, kind, result)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    kind = "reference" if po.have_reference() else "port"
+    sub = batch.slice(0, n_scen)
+    t0 = time.perf_counter()
+    r = po.solve_batch("cub", sub, weights, mode=0, nthreads=threads, kind=kind)
+    return time.perf_counter() - t0, kind, r
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU code, all host threads, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from spectral_b200.scenarios import GOLDEN_W_CUB, config2
+    cores = os.cpu_count() or 1
+    sample = 256
+    batch = config2(BATCH)
+    times = []
+    kind = "port"
+    for i in range(args.warmup + args.steps):
+        dt, kind, _ = _cpu_reference(batch, GOLDEN_W_CUB, sample, 0)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": SEED_NOTE, "batch_per_gpu": BATCH, "variant": "cub", "n_knots": 71, "n_regions": 2},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "first %d scenarios of the 1024-scenario batch per step, OSQP settings of the "
+                                       "reference (eps 1e-5, max_iter 5000), OpenMP over scenarios" % sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spectral_b200 import api
+    from spectral_b200.scenarios import GOLDEN_W_CUB, config2
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, POOL = BATCH, args.pool
+    k_max = 16
+    planner = api.SpectralPlanner(device=local, max_batch=B, n_max=128, r_max=8, k_max=k_max)
+    # ---- synthetic inputs: POOL distinct batches per rank, resident in HBM
+    first = rank * POOL * B
+    big = config2(POOL * B, first=first)
+    N, R, delta = big.n_knots, big.n_regions, big.delta_t
+    names = ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars")
+    host = {k: np.ascontiguousarray(a) for k, a in zip(names, big.arrays())}
+    resident = {k: torch.from_numpy(a).to(dev) for k, a in host.items()}
+    w_dev = torch.tensor(GOLDEN_W_CUB, dtype=torch.float64, device=dev)
+    outs = [planner.alloc_device_outputs(B) for _ in range(POOL)]
+    best_cost = torch.zeros(1, dtype=torch.float64, device=dev)
+    best_idx = torch.zeros(1, dtype=torch.int64, device=dev)
+    in_bytes = sum(a.nbytes for a in host.values()) // POOL
+    out_bytes = sum(t.numel() * t.element_size() for t in outs[0].values())
+    pool_mb = POOL * (in_bytes + out_bytes) / 1e6
+
+    def slot_inputs(i):
+        d = {k: t[i * B:(i + 1) * B] for k, t in resident.items()}
+        d["weights"] = w_dev
+        return d
+
+    slots = [slot_inputs(i) for i in range(POOL)]
+    gather_buf = torch.zeros(world, 2, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step(i):
+        s = i % POOL
+        planner.solve_device("cub", N, R, delta, slots[s], outs[s])
+        planner.argmin_device(outs[s]["a_cost"], first + s * B, best_cost, best_idx)
+        if world > 1:  # the path's only exchange: (cost, index) arg-min gather
+            mine = torch.stack([best_cost[0], best_idx[0].to(torch.float64)])
+            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    planner.get_work(reset=True)
+    l0 = planner.launch_count()
+    planner.set_timing(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kt = planner.get_timing()
+    planner.set_timing(False)
+    work = planner.get_work(reset=True)
+    launches = planner.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end: host (pinned) buffers through spectral_solve_batch, H2D + kernels + D2H per step
+    pin = {k: torch.from_numpy(a).pin_memory() for k, a in host.items()}
+    pin_np = {k: t.numpy() for k, t in pin.items()}
+    from spectral_b200.wire import ScenarioBatch
+
+    def host_batch(i):
+        s = i % POOL
+        return ScenarioBatch(N, R, delta, *[pin_np[k][s * B:(s + 1) * B] for k in names])
+
+    hb = [host_batch(i) for i in range(POOL)]
+    w_host = np.array(GOLDEN_W_CUB)
+    for i in range(max(3, args.warmup)):
+        res = planner.solve("cub", hb[i % POOL], w_host)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = planner.solve("cub", hb[(args.warmup + i) % POOL], w_host)
+        _ = float(res.a_cost.min())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t_e.item())
+    d2h = sum(getattr(res, f).nbytes for f in ("K", "segs", "ctrl", "obj", "a_cost", "status", "iters", "flags", "npts"))
+    solved_frac = work["solved"] / max(work["scenarios"], 1.0)
+
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        fp64_peak = planner.measure_fp64_peak()
+        calls = max(kt["calls"], 1)
+        qp_ms = kt["qp"] / calls            # mean per step (3 lane-class launches, <= k_max/8 of them non-empty)
+        cor_ms = kt["corridor"] / calls
+        steps_counted = max(args.steps, 1)
+        flops_per_step = work["admm_flops"] / steps_counted
+        iters_per_step = work["admm_iters"] / steps_counted
+        achieved_tf = flops_per_step / (qp_ms * 1e-3) / 1e12 if qp_ms > 0 else 0.0
+        cor_bytes = B * (8 * (4 * R * N + 2 * N) + 112 * 8 + 4)  # bounds + refs in, K cubes + K out
+        cor_gbs = cor_bytes / (cor_ms * 1e-3) / 1e9 if cor_ms > 0 else 0.0
+        # CPU baseline: bounded sample of the same workload on the host cores
+        cpu_sample = 128
+        dt, kind, _ = _cpu_reference(hb[0], w_host, cpu_sample, 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": SEED_NOTE, "batch_per_gpu": B, "variant": "cub", "n_knots": N, "n_regions": R,
+                       "k_max": k_max, "l2": "inputs larger than L2: pool of %d distinct batches, %.0f MB in+out per rank" % (POOL, pool_mb),
+                       "solved_fraction": solved_frac, "admm_iters_per_s": world * iters_per_step / (ms_max / args.steps * 1e-3),
+                       "mean_axis_iters": iters_per_step / (2 * B)},
+            "roofline": {"kernel": "k_qp (batched ADMM + polish)", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "FP64 FMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "ms_per_launch_group": qp_ms, "flops_per_step": flops_per_step},
+            "roofline_corridor": {"kernel": "k_corridor", "bound": "hbm", "achieved": cor_gbs, "peak": peaks.get("hbm_gbs"),
+                                  "unit": "GB/s", "frac": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                  "traffic": None, "peak_source": peak_src, "ms_per_launch": cor_ms},
+            "kernel_ms_per_step": {k: kt[k] / calls for k in ("tables", "corridor", "classify", "qp", "finalize")},
+            "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                             "sample": "first %d scenarios of one 1024-scenario batch, reference OSQP settings" % cpu_sample},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--pool", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

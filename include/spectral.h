@@ -155,10 +155,18 @@ long long spectral_launch_count(const spectral_handle_t *h);
  * roofline denominator of the ADMM kernel because MEASURED_PEAKS.json has no FP64 entry). */
 int spectral_measure_fp64_peak(spectral_handle_t *h, double *tflops);
 
-/* Device time (ms) spent in each kernel class during the last solve_batch*_ call with timing enabled. */
-#define SPECTRAL_NUM_KERNELS 6 /* tables, corridor, classify, qp, finalize, argmin */
+/* Per-kernel-class device time, measured with CUDA events recorded on the launching stream around every
+ * kernel class of each solve_batch*_ call while timing is enabled.  Nothing synchronises inside the
+ * calls; spectral_get_timing() waits for the recorded events and returns the SUM of milliseconds per
+ * class over the last `*calls` (<= 64) calls since spectral_set_timing(h, 1). */
+#define SPECTRAL_NUM_KERNELS 6 /* tables, corridor, classify, qp, finalize, (argmin: not timed) */
 int spectral_set_timing(spectral_handle_t *h, int enabled);
-int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS]);
+int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS], int *calls);
+
+/* Work counters accumulated on the device by every solve_batch*_ call (synchronises the device):
+ * work[0] ADMM iterations summed over axis problems, work[1] their algorithmic flops
+ * ((424 K - 168) per axis-iteration), work[2] scenarios processed, work[3] scenarios solved. */
+int spectral_get_work(spectral_handle_t *h, double work[4], int reset);
 
 /* The reference's plugin entry point (exported by libtrp.so / libcub.so, not by libspectral.so):
  *   double find_traj(SpectralParams *p);                       trp_wrapper.cpp:20, cub_wrapper.cpp:19 */

@@ -107,7 +107,8 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_launch_count.restype = ctypes.c_longlong
     lib.spectral_measure_fp64_peak.argtypes = [ctypes.c_void_p, _dp]
     lib.spectral_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    lib.spectral_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    lib.spectral_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), _ip]
+    lib.spectral_get_work.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int]
     _lib = lib
     return lib
 
@@ -264,9 +265,18 @@ class SpectralPlanner:
         self._check(self._lib.spectral_set_timing(self._h, 1 if on else 0))
 
     def get_timing(self) -> dict:
+        """Summed device ms per kernel class over the calls recorded since set_timing(True), plus 'calls'."""
         ms = (ctypes.c_float * NUM_KERNELS)()
-        self._check(self._lib.spectral_get_timing(self._h, ms))
-        return {k: float(ms[i]) for i, k in enumerate(KERNEL_NAMES)}
+        calls = ctypes.c_int()
+        self._check(self._lib.spectral_get_timing(self._h, ms, ctypes.byref(calls)))
+        out = {k: float(ms[i]) for i, k in enumerate(KERNEL_NAMES)}
+        out["calls"] = calls.value
+        return out
+
+    def get_work(self, reset: bool = False) -> dict:
+        w = (ctypes.c_double * 4)()
+        self._check(self._lib.spectral_get_work(self._h, w, 1 if reset else 0))
+        return dict(admm_iters=w[0], admm_flops=w[1], scenarios=w[2], solved=w[3])
 
 
 # ------------------------------------------------------------------ the reference's plugin surface

@@ -75,9 +75,30 @@ __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   qp_warp_body<LPA>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
 }
 
-__global__ void k_finalize(const FinalArgs a) {
+// `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:
+//   work[0] += ADMM iterations summed over the axis problems of this batch
+//   work[1] += algorithmic flops of those iterations, (424 K - 168) per axis-iteration
+//   work[2] += scenarios processed,  work[3] += scenarios solved
+__global__ void k_finalize(const FinalArgs a, double *work) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) finalize_body(a, b);
+  double it = 0.0, fl = 0.0, ok = 0.0, cnt = 0.0;
+  if (b < a.B) {
+    finalize_body(a, b);
+    cnt = 1.0;
+    if (a.cstatus[b] == 0) {
+      it = (double)a.axis_iters[2 * b] + (double)a.axis_iters[2 * b + 1];
+      fl = it * (424.0 * a.K[b] - 168.0);
+      const int s0 = a.axis_status[2 * b], s1 = a.axis_status[2 * b + 1];
+      ok = ((s0 == QP_ST_SOLVED || s0 == QP_ST_INACCURATE) && (s1 == QP_ST_SOLVED || s1 == QP_ST_INACCURATE)) ? 1.0 : 0.0;
+    }
+  }
+  for (int m = 16; m > 0; m >>= 1) {
+    it += __shfl_xor_sync(0xffffffffu, it, m); fl += __shfl_xor_sync(0xffffffffu, fl, m);
+    ok += __shfl_xor_sync(0xffffffffu, ok, m); cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+    atomicAdd(&work[0], it); atomicAdd(&work[1], fl); atomicAdd(&work[2], cnt); atomicAdd(&work[3], ok);
+  }
 }
 
 // K6: (min cost, lowest index) -- two-stage, last block finishes (ticket)
@@ -147,8 +168,10 @@ struct spectral_handle {
   std::string err;
   long long launches = 0;
   bool timing = false;
-  cudaEvent_t ev[SPECTRAL_NUM_KERNELS + 1] = {};
-  float ms[SPECTRAL_NUM_KERNELS] = {};
+  static const int kTimingSlots = 64;  // ring of per-call event sets; nothing synchronises until get_timing
+  cudaEvent_t ev[kTimingSlots][SPECTRAL_NUM_KERNELS + 1] = {};
+  long long timed_calls = 0;
+  double *work = nullptr;  // device counters, see k_finalize
   // intermediates
   int *cstatus = nullptr, *lists = nullptr, *counts = nullptr, *axis_status = nullptr, *axis_iters = nullptr,
       *axis_polished = nullptr;
@@ -215,7 +238,10 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   CK(cudaMalloc(&h->partial, 1024 * sizeof(ArgminPair)));
   CK(cudaMalloc(&h->ticket, 4));
   CK(cudaMemset(h->ticket, 0, 4));
-  for (auto &e : h->ev) CK(cudaEventCreate(&e));
+  CK(cudaMalloc(&h->work, 4 * 8));
+  CK(cudaMemset(h->work, 0, 4 * 8));
+  for (auto &slot : h->ev)
+    for (auto &e : slot) CK(cudaEventCreate(&e));
   return SPECTRAL_SUCCESS;
 }
 
@@ -223,11 +249,12 @@ extern "C" int spectral_destroy(spectral_handle_t *h) {
   if (!h) return SPECTRAL_ERR_INVALID;
   cudaSetDevice(h->device);
   void *bufs[] = {h->cstatus, h->lists, h->counts, h->axis_status, h->axis_iters, h->axis_polished, h->axis_obj, h->mqm,
-                  h->partial, h->ticket, h->d_K, h->d_status, h->d_iters, h->d_flags, h->d_npts, h->d_segs, h->d_ctrl,
+                  h->partial, h->ticket, h->work, h->d_K, h->d_status, h->d_iters, h->d_flags, h->d_npts, h->d_segs, h->d_ctrl,
                   h->d_obj, h->d_cost, h->d_samples, h->d_lu};
   for (void *p : bufs) if (p) cudaFree(p);
   for (auto p : h->d_in) if (p) cudaFree(p);
-  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto &slot : h->ev)
+    for (auto &e : slot) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return SPECTRAL_SUCCESS;
@@ -236,11 +263,31 @@ extern "C" int spectral_destroy(spectral_handle_t *h) {
 extern "C" int spectral_set_timing(spectral_handle_t *h, int enabled) {
   if (!h) return SPECTRAL_ERR_INVALID;
   h->timing = enabled != 0;
+  h->timed_calls = 0;
   return SPECTRAL_SUCCESS;
 }
-extern "C" int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS]) {
-  if (!h) return SPECTRAL_ERR_INVALID;
-  memcpy(ms, h->ms, sizeof(h->ms));
+extern "C" int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS], int *calls) {
+  if (!h || !ms) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int n = (int)(h->timed_calls < spectral_handle::kTimingSlots ? h->timed_calls : spectral_handle::kTimingSlots);
+  for (int k = 0; k < SPECTRAL_NUM_KERNELS; k++) ms[k] = 0.f;
+  for (int s = 0; s < n; s++) {
+    CK(cudaEventSynchronize(h->ev[s][SPECTRAL_NUM_KERNELS - 1]));
+    for (int k = 0; k < SPECTRAL_NUM_KERNELS - 1; k++) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, h->ev[s][k], h->ev[s][k + 1]));
+      ms[k] += t;
+    }
+  }
+  if (calls) *calls = n;
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_get_work(spectral_handle_t *h, double work[4], int reset) {
+  if (!h || !work) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(work, h->work, 4 * 8, cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(h->work, 0, 4 * 8));
   return SPECTRAL_SUCCESS;
 }
 
@@ -270,14 +317,15 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   SpectralOptions opt;
   if (opt_in) opt = *opt_in; else spectral_default_options(&opt);
   const bool tm = h->timing;
+  cudaEvent_t *ev = h->ev[h->timed_calls % spectral_handle::kTimingSlots];
   int evi = 0;
-  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+  if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K3a: weight tables
   const int W = in->weights_stride ? B : 1;
   k_tables<<<(2 * W + 127) / 128, 128, 0, st>>>(in->weights, h->mqm, W);
   h->launches++;
-  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+  if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K1 + K2: corridors
   CorridorArgs ca{B, N, R, variant, h->k_max, delta_t, in->s_bounds, in->l_bounds, in->s_ref, in->l_ref, out->segs, out->K, h->cstatus};
@@ -285,14 +333,14 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   spectral_launch_corridor(ca, st);
   h->launches++;
   CK(cudaGetLastError());
-  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+  if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // classification by segment count -> lane class lists
   CK(cudaMemsetAsync(h->counts, 0, 16, st));
   if (B <= 4096) k_classify_ordered<<<1, 1024, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   else k_classify<<<(B + 255) / 256, 256, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   h->launches++;
-  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+  if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K3 + K4b: QP per lane class
   QpArgs qa;
@@ -317,7 +365,7 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
     qa.list = h->lists + 2 * (size_t)B; qa.count = h->counts + 2;
     CK((launch_qp<32, 2>(h, qa, B, st)));
   }
-  if (tm) CK(cudaEventRecord(h->ev[evi++], st));
+  if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K5: sampling + cost + status merge
   FinalArgs fa;
@@ -326,13 +374,12 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   fa.cstatus = h->cstatus; fa.axis_status = h->axis_status; fa.axis_iters = h->axis_iters; fa.axis_polished = h->axis_polished;
   fa.axis_obj = h->axis_obj; fa.ctrl = out->ctrl; fa.obj = out->obj; fa.a_cost = out->a_cost; fa.samples = out->samples;
   fa.status = out->status; fa.iters = out->iters; fa.flags = out->flags; fa.npts = out->npts; fa.samples_cap = out->samples_cap;
-  k_finalize<<<(B + 127) / 128, 128, 0, st>>>(fa);
+  k_finalize<<<(B + 127) / 128, 128, 0, st>>>(fa, h->work);
   h->launches++;
   CK(cudaGetLastError());
   if (tm) {
-    CK(cudaEventRecord(h->ev[evi++], st));
-    CK(cudaEventSynchronize(h->ev[evi - 1]));
-    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&h->ms[i], h->ev[i], h->ev[i + 1]));
+    CK(cudaEventRecord(ev[evi++], st));
+    h->timed_calls++;
   }
   return SPECTRAL_SUCCESS;
 }

@@ -1,0 +1,126 @@
+"""Shared test helpers: golden loading, the kernel-logic emulator binding, parity comparisons."""
+import ctypes
+import os
+
+import numpy as np
+
+from spectral_b200 import api
+from spectral_b200.scenarios import load_fixture
+from spectral_b200.wire import ScenarioBatch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star tolerance for the floating-point part of the path (control points, costs)
+RTOL, ATOL = 1e-5, 1e-6
+
+ALL_FIXTURES = ("c1", "c2", "c3", "c4", "c4_2", "c5", "c6", "c7", "c7_7", "c7_10", "c_road_s1", "c_road_s1_2",
+                "c_road_s1_3", "bounds")
+VARIANTS = ("trp", "cub")
+
+_npz = {}
+
+
+def golden(name):
+    if name not in _npz:
+        _npz[name] = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return _npz[name]
+
+
+def fixture_batch(name):
+    return ScenarioBatch.from_scenarios([load_fixture(name)])
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return bool(np.all(np.abs(a - b) <= atol + rtol * np.abs(b)))
+
+
+def maxdiff(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+def segs_equal(a, b, K):
+    """Bit-exact comparison of the first K cubes (every field incl. the defaulted ones)."""
+    return a[:K].tobytes() == b[:K].tobytes()
+
+
+def lu_to_qp_rows(lu, K):
+    """[2, k_max, 21, 2] lane-major (l,u) rows -> the reference's row order (a7): per axis
+    K x 18 segment rows, 3 initial-state rows, then 3 rows per joint.  Returns (l[42K], u[42K])."""
+    out = []
+    for axis in range(2):
+        seg_rows = lu[axis, :K, :18].reshape(K * 18, 2)
+        init_rows = lu[axis, 0, 18:21]
+        joint_rows = lu[axis, 1:K, 18:21].reshape((K - 1) * 3, 2)
+        out.append(np.concatenate([seg_rows, init_rows, joint_rows], axis=0))
+    allrows = np.concatenate(out, axis=0)
+    return allrows[:, 0].copy(), allrows[:, 1].copy()
+
+
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        _emu = ctypes.CDLL(os.path.join(ROOT, "tests", "warp_emu", "libwarp_emu.so"))
+    return _emu
+
+
+def emu_solve(variant, batch, weights, k_max=32, samples_cap=0, want_lu=False, **opts):
+    """Run the kernels' device bodies on the host (32 lock-stepped threads per warp).  Slow: tiny batches only."""
+    emu = emu_lib()
+    B = batch.batch
+    o = api.SpectralOptions()
+    emu.emu_default_options(ctypes.byref(o))
+    for k, v in opts.items():
+        setattr(o, k, v)
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in batch.arrays()]
+    res = api.BatchResult(np.zeros(B, np.int32), np.zeros((B, k_max), api.CUBE_DTYPE), np.zeros((B, 12 * k_max)),
+                          np.zeros(B), np.zeros(B), np.zeros(B, np.int32), np.zeros(B, np.int32),
+                          np.zeros(B, np.int32), np.zeros(B, np.int32),
+                          np.zeros((B, samples_cap, 6)) if samples_cap else None,
+                          np.zeros((B, 2, k_max, 21, 2)) if want_lu else None)
+    d, i = api._d, api._i
+    emu.emu_solve_batch(api.VARIANT_ID[variant], B, batch.n_knots, batch.n_regions, ctypes.c_double(batch.delta_t),
+                        *[d(a) for a in arrs], d(w), 0 if w.ndim == 1 else 1, k_max, ctypes.byref(o), i(res.K),
+                        res.segs.ctypes.data_as(ctypes.c_void_p), d(res.ctrl), d(res.obj), d(res.a_cost),
+                        i(res.status), i(res.iters), i(res.flags), i(res.npts), d(res.samples), samples_cap,
+                        d(res.lu))
+    return res
+
+
+def assert_batch_parity(got, ref, label="", need_verified_frac=0.0):
+    """got: api.BatchResult (GPU or emulator); ref: pyoracle.solve_batch(mode=1) dict (converged oracle).
+    Integer/struct outputs bit-exact; floating outputs within RTOL/ATOL where both sides hold the
+    KKT-verified optimum; success/failure classes identical."""
+    B = len(got.K)
+    assert np.array_equal(got.K, ref["K"]), "%s: K differs at %s" % (label, np.nonzero(got.K != ref["K"])[0][:8])
+    for b in range(B):
+        K = int(got.K[b])
+        if ref["status"][b] in (2, 5):
+            continue
+        assert segs_equal(got.segs[b], ref["segs"][b], K), "%s: segs differ at scenario %d" % (label, b)
+    corridor_fail = np.isin(ref["status"], (2, 5))
+    assert np.array_equal(got.status[corridor_fail], ref["status"][corridor_fail]), label
+    ok_ref = ref["status"] <= 1
+    assert np.array_equal(got.ok(), ok_ref), "%s: ok/fail classes differ at %s (got %s, ref %s)" % (
+        label, np.nonzero(got.ok() != ok_ref)[0][:8], got.status[got.ok() != ok_ref][:8],
+        ref["status"][got.ok() != ok_ref][:8])
+    both = got.verified() & ok_ref & (ref["polish"] == 2)
+    if ok_ref.any():
+        frac = both.sum() / ok_ref.sum()
+        assert frac >= need_verified_frac, "%s: only %.3f of the solved scenarios are KKT-verified on both sides" % (label, frac)
+    for b in np.nonzero(both)[0]:
+        K = int(got.K[b])
+        assert close(got.ctrl[b, :12 * K], ref["ctrl"][b, :12 * K]), "%s: ctrl of scenario %d off by %.3e" % (
+            label, b, maxdiff(got.ctrl[b, :12 * K], ref["ctrl"][b, :12 * K]))
+        assert close(got.obj[b], ref["obj"][b], rtol=1e-8, atol=1e-6), (label, b, got.obj[b], ref["obj"][b])
+        assert close(got.a_cost[b], ref["a_cost"][b]), (label, b, got.a_cost[b], ref["a_cost"][b])
+        assert got.npts[b] == ref["npts"][b]
+    fail = ~got.ok()
+    assert np.all(got.a_cost[fail] == api.FAIL_COST), label
+    return both

@@ -41,9 +41,19 @@ def maxdiff(a, b):
     return float(np.max(np.abs(a - b))) if a.size else 0.0
 
 
+SEG_FIELDS = ("beg_t", "end_t", "t", "beg_l", "end_l", "upp_skew", "upp_bias", "down_skew", "down_bias",
+              "l_upp_skew", "l_upp_bias", "l_down_skew", "l_down_bias", "merge", "split")
+
+
 def segs_equal(a, b, K):
-    """Bit-exact comparison of the first K cubes (every field incl. the defaulted ones)."""
-    return a[:K].tobytes() == b[:K].tobytes()
+    """Bit-exact comparison of the first K cubes on every field the reference's Cube() initialises or the
+    path writes.  (`t_dif` is never initialised by the reference -- cube_type.h:12-21 -- and `count` is
+    bookkeeping of CollisionCheck's push loop; both are unused downstream.)"""
+    a, b = np.asarray(a)[:K], np.asarray(b)[:K]
+    for f in SEG_FIELDS:
+        if a[f].tobytes() != b[f].tobytes():
+            return False
+    return True
 
 
 def lu_to_qp_rows(lu, K):
@@ -93,10 +103,11 @@ def emu_solve(variant, batch, weights, k_max=32, samples_cap=0, want_lu=False, *
     return res
 
 
-def assert_batch_parity(got, ref, label="", need_verified_frac=0.0):
-    """got: api.BatchResult (GPU or emulator); ref: pyoracle.solve_batch(mode=1) dict (converged oracle).
+def assert_batch_parity(got, ref, label="", need_verified_frac=0.0, ref0=None, max_status_mismatch=0):
+    """got: api.BatchResult (GPU or emulator); ref: pyoracle.solve_batch(mode=1) dict (converged oracle);
+    ref0: pyoracle.solve_batch(mode=0) dict (the reference's own OSQP settings: decides solved / failed).
     Integer/struct outputs bit-exact; floating outputs within RTOL/ATOL where both sides hold the
-    KKT-verified optimum; success/failure classes identical."""
+    KKT-verified optimum; success/failure classes identical to the reference-settings run."""
     B = len(got.K)
     assert np.array_equal(got.K, ref["K"]), "%s: K differs at %s" % (label, np.nonzero(got.K != ref["K"])[0][:8])
     for b in range(B):
@@ -106,11 +117,12 @@ def assert_batch_parity(got, ref, label="", need_verified_frac=0.0):
         assert segs_equal(got.segs[b], ref["segs"][b], K), "%s: segs differ at scenario %d" % (label, b)
     corridor_fail = np.isin(ref["status"], (2, 5))
     assert np.array_equal(got.status[corridor_fail], ref["status"][corridor_fail]), label
-    ok_ref = ref["status"] <= 1
-    assert np.array_equal(got.ok(), ok_ref), "%s: ok/fail classes differ at %s (got %s, ref %s)" % (
-        label, np.nonzero(got.ok() != ok_ref)[0][:8], got.status[got.ok() != ok_ref][:8],
-        ref["status"][got.ok() != ok_ref][:8])
-    both = got.verified() & ok_ref & (ref["polish"] == 2)
+    st0 = (ref0 if ref0 is not None else ref)["status"]
+    ok_ref = st0 <= 1
+    mism = got.ok() != ok_ref
+    assert mism.sum() <= max_status_mismatch, "%s: ok/fail classes differ at %d scenarios %s (got %s, ref %s)" % (
+        label, mism.sum(), np.nonzero(mism)[0][:8], got.status[mism][:8], st0[mism][:8])
+    both = got.verified() & (ref["status"] <= 1) & (ref["polish"] == 2)
     if ok_ref.any():
         frac = both.sum() / ok_ref.sum()
         assert frac >= need_verified_frac, "%s: only %.3f of the solved scenarios are KKT-verified on both sides" % (label, frac)
@@ -124,3 +136,10 @@ def assert_batch_parity(got, ref, label="", need_verified_frac=0.0):
     fail = ~got.ok()
     assert np.all(got.a_cost[fail] == api.FAIL_COST), label
     return both
+
+
+def oracle_pair(variant, batch, weights, nthreads=0):
+    """(converged oracle, reference-settings oracle) for one batch."""
+    import pyoracle as po
+    return (po.solve_batch(variant, batch, weights, mode=1, nthreads=nthreads),
+            po.solve_batch(variant, batch, weights, mode=0, nthreads=nthreads))

@@ -114,8 +114,8 @@ def test_config2_cub_1024_vs_oracle(planner):
     """BASELINE configs[1]: 1024 obstacle-perturbed copies of scenario_1, cuboid variant."""
     batch = config2(1024)
     got = planner.solve("cub", batch, GOLDEN_W_CUB, samples_cap=160)
-    ref = po.solve_batch("cub", batch, GOLDEN_W_CUB, mode=1, nthreads=0)
-    both = H.assert_batch_parity(got, ref, "config2", need_verified_frac=0.9)
+    ref, ref0 = H.oracle_pair("cub", batch, GOLDEN_W_CUB)
+    both = H.assert_batch_parity(got, ref, "config2", need_verified_frac=0.9, ref0=ref0)
     for b in np.nonzero(both)[0][:64]:
         n = int(got.npts[b])
         assert H.close(got.samples[b, :n], ref["samples"][b, :n], rtol=1e-5, atol=2e-6)
@@ -124,16 +124,16 @@ def test_config2_cub_1024_vs_oracle(planner):
 def test_config2_trp_512_vs_oracle(planner):
     batch = perturbed_obstacles(load_fixture("c1"), 512, seed=77)
     got = planner.solve("trp", batch, GOLDEN_W_TRP)
-    ref = po.solve_batch("trp", batch, GOLDEN_W_TRP, mode=1, nthreads=0)
-    H.assert_batch_parity(got, ref, "trp512", need_verified_frac=0.9)
+    ref, ref0 = H.oracle_pair("trp", batch, GOLDEN_W_TRP)
+    H.assert_batch_parity(got, ref, "trp512", need_verified_frac=0.9, ref0=ref0)
 
 
 def test_mixed_variable_structure_vs_oracle(planner):
     """config 4 shape at test size: heterogeneous K, both variants."""
     for variant, batch in mixed_batches(640, seed=20230602):
         got = planner.solve(variant, batch, WEIGHTS_FILE)
-        ref = po.solve_batch(variant, batch, WEIGHTS_FILE, mode=1, nthreads=0)
-        H.assert_batch_parity(got, ref, "mixed/%s" % variant, need_verified_frac=0.8)
+        ref, ref0 = H.oracle_pair(variant, batch, WEIGHTS_FILE)
+        H.assert_batch_parity(got, ref, "mixed/%s" % variant, need_verified_frac=0.8, ref0=ref0)
 
 
 def test_per_scenario_weights(planner):
@@ -143,16 +143,16 @@ def test_per_scenario_weights(planner):
     w[:, :4] = rng.uniform(1.0, 50.0, (256, 4))
     w[:, 5] = rng.uniform(1.0, 50.0, 256)
     got = planner.solve("cub", batch, w)
-    ref = po.solve_batch("cub", batch, w, mode=1, nthreads=0)
-    H.assert_batch_parity(got, ref, "weights", need_verified_frac=0.8)
+    ref, ref0 = H.oracle_pair("cub", batch, w)
+    H.assert_batch_parity(got, ref, "weights", need_verified_frac=0.8, ref0=ref0)
 
 
 def test_edge_cases(planner):
     # B = 1, minimal horizon that still yields a corridor, R = 1
     sc = load_fixture("c2")
     got = planner.solve("trp", ScenarioBatch.from_scenarios([sc]), WEIGHTS_FILE)
-    ref = po.solve_batch("trp", ScenarioBatch.from_scenarios([sc]), WEIGHTS_FILE, mode=1)
-    H.assert_batch_parity(got, ref, "c2")
+    ref, ref0 = H.oracle_pair("trp", ScenarioBatch.from_scenarios([sc]), WEIGHTS_FILE)
+    H.assert_batch_parity(got, ref, "c2", ref0=ref0)
     # a scenario whose reference trajectory lies outside every cube -> nothing selected
     far = load_fixture("c1")
     far.l_ref = far.l_ref + 100.0
@@ -201,10 +201,10 @@ def test_full_size_properties_65536(planner):
     # spot-check 256 random scenarios against the oracle
     idx = np.sort(np.random.default_rng(1).choice(B, 256, replace=False))
     sub = ScenarioBatch(batch.n_knots, batch.n_regions, batch.delta_t, *[x[idx] for x in batch.arrays()])
-    ref = po.solve_batch("trp", sub, WEIGHTS_FILE, mode=1, nthreads=0)
+    ref, ref0 = H.oracle_pair("trp", sub, WEIGHTS_FILE)
     g = api.BatchResult(a.K[idx], a.segs[idx], a.ctrl[idx], a.obj[idx], a.a_cost[idx], a.status[idx], a.iters[idx],
                         a.flags[idx], a.npts[idx])
-    H.assert_batch_parity(g, ref, "spot65536", need_verified_frac=0.8)
+    H.assert_batch_parity(g, ref, "spot65536", need_verified_frac=0.8, ref0=ref0)
 
 
 # ---------------------------------------------------------------- resident path + argmin

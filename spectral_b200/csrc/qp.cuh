@@ -134,6 +134,7 @@ SP_DEV void apply_AT(const double v[QP_ROWS], double n18, double n19, double n20
 }
 
 // y = P_k x with P_k packed lower triangle in shared memory
+template <int STR>
 SP_DEV void apply_P(const double *sm, int lane, const double x[6], double y[6]) {
 #pragma unroll
   for (int i = 0; i < 6; i++) y[i] = 0.0;
@@ -141,7 +142,7 @@ SP_DEV void apply_P(const double *sm, int lane, const double x[6], double y[6]) 
   for (int i = 0; i < 6; i++)
 #pragma unroll
     for (int j = 0; j <= i; j++) {
-      double p = sm[(QP_SM_P + LT(i, j)) * 32 + lane];
+      double p = sm[(QP_SM_P + LT(i, j)) * STR + lane];
       y[i] += p * x[j];
       if (i != j) y[j] += p * x[i];
     }
@@ -156,7 +157,7 @@ struct QpFactor {
 
 // Builds S from (P block in smem, sig[6], rho[21] in smem slot `rho_slot`) and factorises it.
 // Returns 0 on success, 1 if a pivot was not positive (lane-local flag; caller reduces).
-template <int LPA>
+template <int LPA, int STR>
 // pol_scale == 0: ADMM mode, row penalty = rho slot.  pol_scale > 0: polish mode, row penalty =
 // rho slot * pol_scale (/1e3 on equality rows) on the rows of `actmask`, zero elsewhere.
 SP_DEV int qp_factorize(const double *sm, int lane, int rho_slot, const double sig[6], double t, double tp, double tn,
@@ -167,13 +168,13 @@ SP_DEV int qp_factorize(const double *sm, int lane, int rho_slot, const double s
 #pragma unroll
   for (int i = 0; i < 6; i++)
 #pragma unroll
-    for (int j = 0; j <= i; j++) S[LT(i, j)] = sm[(QP_SM_P + LT(i, j)) * 32 + lane] + (i == j ? sig[i] : 0.0);
+    for (int j = 0; j <= i; j++) S[LT(i, j)] = sm[(QP_SM_P + LT(i, j)) * STR + lane] + (i == j ? sig[i] : 0.0);
 #pragma unroll
   for (int e = 0; e < 9; e++) Bo[e] = 0.0;
   double rj[3];
 #pragma unroll
   for (int r = 0; r < QP_ROWS; r++) {
-    double rho = sm[(rho_slot + r) * 32 + lane];
+    double rho = sm[(rho_slot + r) * STR + lane];
     if (pol_scale > 0.0) rho = ((actmask >> r) & 1u) ? rho * pol_scale * (((eqmask >> r) & 1u) ? 1e-3 : 1.0) : 0.0;
     if (r >= 18) rj[r - 18] = rho;
 #pragma unroll
@@ -367,8 +368,9 @@ struct QpResid {
   double pri, dua, nz, nax, nq, npx, naty;
 };
 
-// residuals of (x, w) in OSQP's scaled space; z = clip(w), y = rho (w - z)
-template <int LPA>
+// residuals of (x, w) in OSQP's scaled space; z = clip(w), y = rho (w - z).  RW = reduction width:
+// LPA for one axis problem, 2*LPA for the joint (s, l) problem held by two adjacent lane groups.
+template <int LPA, int STR, int RW>
 SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const double q[6], const double cD[6],
                             double c_over_rhobar, unsigned eqmask, double t, double tp, double tn, bool first, bool last,
                             bool active) {
@@ -380,8 +382,8 @@ SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const
   double pri = 0.0, nz = 0.0, nax = 0.0;
 #pragma unroll
   for (int r = 0; r < QP_ROWS; r++) {
-    const double w = sm[(QP_SM_W + r) * 32 + lane], l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
-    const double rho = sm[(QP_SM_RHO + r) * 32 + lane];
+    const double w = sm[(QP_SM_W + r) * STR + lane], l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
+    const double rho = sm[(QP_SM_RHO + r) * STR + lane];
     const double z = fmin(fmax(w, l), u);
     y[r] = rho * (w - z);
     const double eqf = ((eqmask >> r) & 1u) ? 1e-3 : 1.0;
@@ -396,7 +398,7 @@ SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const
     if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
     apply_AT(y, n18, n19, n20, t, tp, tn, first, aty);
   }
-  apply_P(sm, lane, x, px);
+  apply_P<STR>(sm, lane, x, px);
   double dua = 0.0, nq = 0.0, npx = 0.0, naty = 0.0;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -407,22 +409,30 @@ SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const
   }
   QpResid R;
   if (!active) { pri = 0; dua = 0; nz = 0; nax = 0; nq = 0; npx = 0; naty = 0; }
-  R.pri = sp_group_max(pri, LPA); R.dua = sp_group_max(dua, LPA); R.nz = sp_group_max(nz, LPA);
-  R.nax = sp_group_max(nax, LPA); R.nq = sp_group_max(nq, LPA); R.npx = sp_group_max(npx, LPA);
-  R.naty = sp_group_max(naty, LPA);
+  R.pri = sp_group_max(pri, RW); R.dua = sp_group_max(dua, RW); R.nz = sp_group_max(nz, RW);
+  R.nax = sp_group_max(nax, RW); R.nq = sp_group_max(nq, RW); R.npx = sp_group_max(npx, RW);
+  R.naty = sp_group_max(naty, RW);
   return R;
 }
 
-// ------------------------------------------------------------------ the warp body
-// One warp = 32/LPA axis problems.  `sm` = this warp's shared-memory slab (QP_SMEM_PER_WARP bytes).
-template <int LPA>
-SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm) {
-  constexpr int G = 32 / LPA;
-  const int cnt = *a.count;
-  const int grp = lane / LPA, seg = lane % LPA;
-  const int ap = warp_global * G + grp;  // axis-problem slot in this class
-  if (warp_global * G >= 2 * cnt) return;
-  const bool have = ap < 2 * cnt;
+// ------------------------------------------------------------------ per-lane problem state
+// Lane-per-segment layout: LPA lanes hold one axis problem, lane `seg` owns segment `seg`.  JW is the
+// joint width: with JW = 2*LPA the s-axis and l-axis problems of one scenario sit in adjacent lane groups
+// and are solved as ONE OSQP instance like the reference does (one cost scaling c, one rho, joint
+// termination / infeasibility norms, solve_3d.cc:1211-1249); with JW = LPA each axis is its own instance.
+struct QpLane {
+  int b, axis, K, seg, kmaxw;
+  bool have, active, first, last;
+  double t, tp, tn;
+  double q[6], sig[6], cD[6];
+  double c, rhobar;
+  unsigned eqmask;
+};
+
+// K3 + Ruiz equilibration + per-row rho: fills the shared-memory slots L, U, W (= 0), P, RHO of this
+// lane and the lane state.  `lane` is the shared-memory column of this lane (slot * STR + lane).
+template <int LPA, int STR, int JW>
+SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, double *sm, QpLane &Q) {
   const int b = have ? a.list[ap >> 1] : 0;
   const int axis = ap & 1;
   const int K = have ? a.K[b] : 0;
@@ -560,14 +570,14 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
     for (int e = 0; e < 21; e++) {
       double v = t3 * mq[e] + t * mq[21 + e] + mq[42 + e] * it + mq[63 + e] * it3;
       if (e == 20 && last) v += wv[8 + axis] * t * t;
-      sm[(QP_SM_P + e) * 32 + lane] = active ? 2.0 * v : (e == LT(0, 0) || e == LT(1, 1) || e == LT(2, 2) || e == LT(3, 3) || e == LT(4, 4) || e == LT(5, 5) ? 1.0 : 0.0);
+      sm[(QP_SM_P + e) * STR + lane] = active ? 2.0 * v : (e == LT(0, 0) || e == LT(1, 1) || e == LT(2, 2) || e == LT(3, 3) || e == LT(4, 4) || e == LT(5, 5) ? 1.0 : 0.0);
     }
   }
 #pragma unroll
   for (int r = 0; r < QP_ROWS; r++) {
-    sm[(QP_SM_L + r) * 32 + lane] = active ? lo[r] : -1.0;
-    sm[(QP_SM_U + r) * 32 + lane] = active ? hi[r] : 1.0;
-    sm[(QP_SM_W + r) * 32 + lane] = 0.0;
+    sm[(QP_SM_L + r) * STR + lane] = active ? lo[r] : -1.0;
+    sm[(QP_SM_U + r) * STR + lane] = active ? hi[r] : 1.0;
+    sm[(QP_SM_W + r) * STR + lane] = 0.0;
   }
   sp_syncwarp();
 
@@ -577,7 +587,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
   for (int j = 0; j < 6; j++) D[j] = 1.0;
 #pragma unroll
   for (int r = 0; r < QP_ROWS; r++) E[r] = 1.0;
-  const double nvars = (double)(6 * K);
+  const double nvars = (double)(6 * K) * (JW / LPA);
   for (int pass = 0; pass < o.scaling; pass++) {
     double cn[6], rn_[QP_ROWS];
     // column norms of [P; A] and row norms of A in the current scaling
@@ -591,7 +601,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       double m = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; i++) {
-        const double p = sm[(QP_SM_P + (i >= j ? LT(i, j) : LT(j, i))) * 32 + lane];
+        const double p = sm[(QP_SM_P + (i >= j ? LT(i, j) : LT(j, i))) * STR + lane];
         m = fmax(m, c * D[i] * fabs(p) * D[j]);
       }
       cn[j] = m;
@@ -629,15 +639,15 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       double m = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; i++) {
-        const double p = sm[(QP_SM_P + (i >= j ? LT(i, j) : LT(j, i))) * 32 + lane];
+        const double p = sm[(QP_SM_P + (i >= j ? LT(i, j) : LT(j, i))) * STR + lane];
         m = fmax(m, c * D[i] * fabs(p) * D[j]);
       }
       colsum += m;
       qn = fmax(qn, c * D[j] * fabs(q[j]));
     }
     if (!active) { colsum = 0.0; qn = 0.0; }
-    colsum = sp_group_sum(colsum, LPA);
-    qn = sp_group_max(qn, LPA);
+    colsum = sp_group_sum(colsum, JW);
+    qn = sp_group_max(qn, JW);
     double ct = colsum / (nvars > 0 ? nvars : 1.0);
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
@@ -652,26 +662,46 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
   for (int j = 0; j < 6; j++) { sig[j] = o.sigma / (c * D[j] * D[j]); cD[j] = c * D[j]; }
 #pragma unroll
   for (int r = 0; r < QP_ROWS; r++) {
-    const bool eq = (E[r] * sm[(QP_SM_U + r) * 32 + lane] - E[r] * sm[(QP_SM_L + r) * 32 + lane]) < 1e-4;  // RHO_TOL, scaled bounds
+    const bool eq = (E[r] * sm[(QP_SM_U + r) * STR + lane] - E[r] * sm[(QP_SM_L + r) * STR + lane]) < 1e-4;  // RHO_TOL, scaled bounds
     if (eq) eqmask |= 1u << r;
-    sm[(QP_SM_RHO + r) * 32 + lane] = rhobar * (eq ? 1e3 : 1.0) * E[r] * E[r] / c;
+    sm[(QP_SM_RHO + r) * STR + lane] = rhobar * (eq ? 1e3 : 1.0) * E[r] * E[r] / c;
   }
   sp_syncwarp();
 
-  QpFactor F;
-  int bad = qp_factorize<LPA>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
-  bad = sp_group_or(bad, LPA);
+  Q.b = b; Q.axis = axis; Q.K = K; Q.seg = seg; Q.kmaxw = kmaxw;
+  Q.have = have; Q.active = active; Q.first = first; Q.last = last;
+  Q.t = t; Q.tp = tp; Q.tn = tn; Q.c = c; Q.rhobar = rhobar; Q.eqmask = eqmask;
+#pragma unroll
+  for (int j = 0; j < 6; j++) { Q.q[j] = q[j]; Q.sig[j] = sig[j]; Q.cD[j] = cD[j]; }
+}
+
+#define QP_UNPACK_LANE(Q)                                                                              \
+  const int b = Q.b, axis = Q.axis, K = Q.K, seg = Q.seg, kmaxw = Q.kmaxw;                             \
+  const bool have = Q.have, active = Q.active, first = Q.first, last = Q.last;                         \
+  const double t = Q.t, tp = Q.tp, tn = Q.tn, c = Q.c;                                                 \
+  const unsigned eqmask = Q.eqmask;                                                                    \
+  const double *q = Q.q, *sig = Q.sig, *cD = Q.cD;                                                     \
+  (void)b; (void)axis; (void)K; (void)seg; (void)kmaxw; (void)have; (void)active; (void)first; (void)last; \
+  (void)t; (void)tp; (void)tn; (void)c; (void)eqmask; (void)q; (void)sig; (void)cD
+
+// The lane-per-segment ADMM loop (OSQP iteration in w form) with the factor F in registers.
+// Used by k_qp (segment counts above the dense kernel's capacity) and as the kernel-logic reference of
+// the dense loop in qp_dense.cuh.
+template <int LPA, int STR, int JW>
+SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q, QpFactor &F, double x[6], int &state,
+                          int &iters) {
+  QP_UNPACK_LANE(Q);
+  double rhobar = Q.rhobar;
+  int bad = qp_factorize<LPA, STR>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
+  bad = sp_group_or(bad, JW);
 
   // ---------------- ADMM (OSQP iteration in w form) ----------------
-  double x[6];
 #pragma unroll
   for (int j = 0; j < 6; j++) x[j] = 0.0;
-  int state = (have && K > 0) ? QP_RUNNING : QP_ST_MAXITER;
+  state = (have && K > 0) ? QP_RUNNING : QP_ST_MAXITER;
   if (bad) state = QP_ST_INFEASIBLE;
-  int iters = 0;
+  iters = 0;
   const double alpha = o.alpha;
-  QpResid last_res;
-  last_res.pri = 0; last_res.dua = 0; last_res.nz = 0; last_res.nax = 0; last_res.nq = 0; last_res.npx = 0; last_res.naty = 0;
 
   for (int it = 1; it <= o.max_iter; it++) {
     if (sp_all(state != QP_RUNNING)) break;
@@ -681,8 +711,8 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
     // v = rho (2 clip(w) - w)  (= rho z - y); first iteration: z = y = 0 exactly as OSQP's cold start
 #pragma unroll
     for (int r = 0; r < QP_ROWS; r++) {
-      const double w = sm[(QP_SM_W + r) * 32 + lane], l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
-      const double rho = sm[(QP_SM_RHO + r) * 32 + lane];
+      const double w = sm[(QP_SM_W + r) * STR + lane], l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
+      const double rho = sm[(QP_SM_RHO + r) * STR + lane];
       const double p = fmin(fmax(w, l), u);
       v[r] = (it == 1) ? 0.0 : rho * (2.0 * p - w);
     }
@@ -706,12 +736,12 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       for (int j = 0; j < 6; j++) x[j] = alpha * xt[j] + (1.0 - alpha) * x[j];
 #pragma unroll
       for (int r = 0; r < QP_ROWS; r++) {
-        const double w = sm[(QP_SM_W + r) * 32 + lane], l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
+        const double w = sm[(QP_SM_W + r) * STR + lane], l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
         const double p = (it == 1) ? 0.0 : fmin(fmax(w, l), u);  // z_prev
         const double wn = (it == 1) ? alpha * v[r] : w + alpha * (v[r] - p);
-        sm[(QP_SM_W + r) * 32 + lane] = wn;
+        sm[(QP_SM_W + r) * STR + lane] = wn;
         if (check) {
-          const double rho = sm[(QP_SM_RHO + r) * 32 + lane];
+          const double rho = sm[(QP_SM_RHO + r) * STR + lane];
           const double yo = (it == 1) ? 0.0 : rho * (w - p);
           const double yn = rho * (wn - fmin(fmax(wn, l), u));
           const double dy = yn - yo;
@@ -725,7 +755,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
     }
     if (run) iters = it;
     if (check) {
-      QpResid R = qp_residuals<LPA>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
+      QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
       const double eps_p = o.eps_abs + o.eps_rel * fmax(R.nz, R.nax);
       const double eps_d = o.eps_abs + o.eps_rel * fmax(R.nq, fmax(R.npx, R.naty));
       int newstate = QP_RUNNING;
@@ -737,8 +767,8 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
 #pragma unroll
           for (int r = 0; r < QP_ROWS; r++) v[r] = 0.0;
         }
-        const double nd = sp_group_max(dy_norm, LPA);
-        const double lhs = sp_group_sum(dy_lhs, LPA);
+        const double nd = sp_group_max(dy_norm, JW);
+        const double lhs = sp_group_sum(dy_lhs, JW);
         double atd[6];
         double n18 = sp_shfl_down(v[18], 1, LPA), n19 = sp_shfl_down(v[19], 1, LPA), n20 = sp_shfl_down(v[20], 1, LPA);
         if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
@@ -747,12 +777,12 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
 #pragma unroll
         for (int j = 0; j < 6; j++) na = fmax(na, fabs(cD[j] * atd[j]));
         if (!active || !run) na = 0.0;
-        na = sp_group_max(na, LPA);
+        na = sp_group_max(na, JW);
         if (R.pri < eps_p && R.dua < eps_d) newstate = QP_ST_SOLVED;
         else if (!(R.pri < eps_p) && nd > o.eps_pinf && lhs < -o.eps_pinf * nd && na < o.eps_pinf * nd)
           newstate = QP_ST_INFEASIBLE;
       }
-      if (run) { last_res = R; state = newstate; }
+      if (run) state = newstate;
       // adaptive rho (OSQP: every adaptive_rho_interval iterations, same residuals)
       if (o.adapt_every > 0 && (it % o.adapt_every == 0)) {
         const bool still = state == QP_RUNNING;
@@ -766,33 +796,47 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
             const double ratio = est / rhobar;
 #pragma unroll
             for (int r = 0; r < QP_ROWS; r++) {
-              const double w = sm[(QP_SM_W + r) * 32 + lane], l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
+              const double w = sm[(QP_SM_W + r) * STR + lane], l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
               const double z = fmin(fmax(w, l), u);
-              sm[(QP_SM_W + r) * 32 + lane] = z + (w - z) / ratio;  // keep (z, y): w' = z + y / rho'
-              sm[(QP_SM_RHO + r) * 32 + lane] *= ratio;
+              sm[(QP_SM_W + r) * STR + lane] = z + (w - z) / ratio;  // keep (z, y): w' = z + y / rho'
+              sm[(QP_SM_RHO + r) * STR + lane] *= ratio;
             }
             rhobar = est;
           }
           sp_syncwarp();
-          int b2 = qp_factorize<LPA>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
-          b2 = sp_group_or(b2, LPA);
+          int b2 = qp_factorize<LPA, STR>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
+          b2 = sp_group_or(b2, JW);
           if (b2 && state == QP_RUNNING) state = QP_ST_INFEASIBLE;
         }
       }
     }
   }
-  // OSQP: at max_iter, accept "solved inaccurate" if 10x looser tolerances hold
-  {
-    QpResid R = qp_residuals<LPA>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
-    if (state == QP_RUNNING) {
-      const double ea = 10.0 * o.eps_abs, er = 10.0 * o.eps_rel;
-      const bool okp = R.pri < ea + er * fmax(R.nz, R.nax);
-      const bool okd = R.dua < ea + er * fmax(R.nq, fmax(R.npx, R.naty));
-      const bool ok0 = R.pri < o.eps_abs + o.eps_rel * fmax(R.nz, R.nax) && R.dua < o.eps_abs + o.eps_rel * fmax(R.nq, fmax(R.npx, R.naty));
-      state = ok0 ? QP_ST_SOLVED : ((okp && okd) ? QP_ST_INACCURATE : QP_ST_MAXITER);
-    }
-    last_res = R;
+  Q.rhobar = rhobar;
+}
+
+// OSQP at max_iter: "solved inaccurate" if the 10x looser tolerances hold (joint norms when JW = 2*LPA)
+SP_DEV int qp_maxiter_state(const SpOptionsDev &o, const QpResid &R) {
+  const double ea = 10.0 * o.eps_abs, er = 10.0 * o.eps_rel;
+  const bool okp = R.pri < ea + er * fmax(R.nz, R.nax);
+  const bool okd = R.dua < ea + er * fmax(R.nq, fmax(R.npx, R.naty));
+  const bool ok0 = R.pri < o.eps_abs + o.eps_rel * fmax(R.nz, R.nax) && R.dua < o.eps_abs + o.eps_rel * fmax(R.nq, fmax(R.npx, R.naty));
+  return ok0 ? QP_ST_SOLVED : ((okp && okd) ? QP_ST_INACCURATE : QP_ST_MAXITER);
+}
+
+// Final status at max_iter, polish and outputs.  Expects the iterate in (x, W slots), the current per-row
+// rho in the RHO slots and Q.rhobar.
+template <int LPA, int STR, int JW>
+SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x[6], int state, int iters) {
+  QP_UNPACK_LANE(Q);
+  const SpOptionsDev &o = a.opt;
+  const double rhobar = Q.rhobar;
+  if (JW != LPA) {
+    QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
+    if (state == QP_RUNNING) state = qp_maxiter_state(o, R);
   }
+  // per-axis residuals of the ADMM iterate: the yardstick of the polish acceptance below
+  QpResid last_res = qp_residuals<LPA, STR, LPA>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
+  if (JW == LPA && state == QP_RUNNING) state = qp_maxiter_state(o, last_res);
 
   // ---------------- polish: exact optimum of the identified active set ----------------
   // Round 0 is OSQP's polish (polish.c): active set guessed from (z, y), equality-constrained KKT
@@ -806,8 +850,8 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
     unsigned lowm = 0, uppm = 0;
 #pragma unroll
     for (int r = 0; r < QP_ROWS; r++) {
-      const double w = sm[(QP_SM_W + r) * 32 + lane], l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
-      const double rho = sm[(QP_SM_RHO + r) * 32 + lane];
+      const double w = sm[(QP_SM_W + r) * STR + lane], l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
+      const double rho = sm[(QP_SM_RHO + r) * STR + lane];
       const double z = fmin(fmax(w, l), u), y = rho * (w - z);
       const double eqf = ((eqmask >> r) & 1u) ? 1e3 : 1.0;  // rho_r = rhobar eqfac E_r^2 / c
       const double kap = eqf * rhobar / rho;                // c / E_r^2
@@ -832,13 +876,13 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       const unsigned actm = lowm | uppm;
       sp_syncwarp();
       QpFactor Fp;
-      badp = qp_factorize<LPA>(sm, lane, QP_SM_RHO, sigp, t, tp, tn, first, last, active, seg, kmaxw, actm, eqmask, pol_scale, Fp);
+      badp = qp_factorize<LPA, STR>(sm, lane, QP_SM_RHO, sigp, t, tp, tn, first, last, active, seg, kmaxw, actm, eqmask, pol_scale, Fp);
       badp = sp_group_or(badp, LPA);
 #pragma unroll
       for (int j = 0; j < 6; j++) xp[j] = 0.0;
       // y_p lives in the W slots from here on (w itself is no longer needed)
 #pragma unroll
-      for (int r = 0; r < QP_ROWS; r++) sm[(QP_SM_W + r) * 32 + lane] = 0.0;
+      for (int r = 0; r < QP_ROWS; r++) sm[(QP_SM_W + r) * STR + lane] = 0.0;
       for (int itp = 0; itp <= o.polish_refine; itp++) {
         double Axp[QP_ROWS], rr[QP_ROWS];
         {
@@ -848,9 +892,9 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
 #pragma unroll
         for (int r = 0; r < QP_ROWS; r++) {
           const bool act = (actm >> r) & 1u;
-          const double yp = sm[(QP_SM_W + r) * 32 + lane];
-          const double rp = act ? sm[(QP_SM_RHO + r) * 32 + lane] * pol_scale * (((eqmask >> r) & 1u) ? 1e-3 : 1.0) : 0.0;
-          const double bnd = ((lowm >> r) & 1u) ? sm[(QP_SM_L + r) * 32 + lane] : sm[(QP_SM_U + r) * 32 + lane];
+          const double yp = sm[(QP_SM_W + r) * STR + lane];
+          const double rp = act ? sm[(QP_SM_RHO + r) * STR + lane] * pol_scale * (((eqmask >> r) & 1u) ? 1e-3 : 1.0) : 0.0;
+          const double bnd = ((lowm >> r) & 1u) ? sm[(QP_SM_L + r) * STR + lane] : sm[(QP_SM_U + r) * STR + lane];
           const double r2 = act ? bnd - Axp[r] : 0.0;
           Axp[r] = r2;             // keep r2
           rr[r] = rp * r2 - yp;    // rho' r2 - y_p
@@ -861,7 +905,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
           if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
           apply_AT(rr, n18, n19, n20, t, tp, tn, first, g);  // A'(rho' r2) - A' y_p
         }
-        apply_P(sm, lane, xp, px);
+        apply_P<STR>(sm, lane, xp, px);
 #pragma unroll
         for (int j = 0; j < 6; j++) g[j] += -q[j] - px[j];
         qp_solve<LPA>(Fp, g, dx, seg, last, kmaxw);
@@ -874,8 +918,8 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
 #pragma unroll
         for (int r = 0; r < QP_ROWS; r++) {
           const bool act = (actm >> r) & 1u;
-          const double rp = sm[(QP_SM_RHO + r) * 32 + lane] * pol_scale * (((eqmask >> r) & 1u) ? 1e-3 : 1.0);
-          if (act) sm[(QP_SM_W + r) * 32 + lane] += rp * (rr[r] - Axp[r]);
+          const double rp = sm[(QP_SM_RHO + r) * STR + lane] * pol_scale * (((eqmask >> r) & 1u) ? 1e-3 : 1.0);
+          if (act) sm[(QP_SM_W + r) * STR + lane] += rp * (rr[r] - Axp[r]);
         }
       }
       // KKT check of the polished point in the scaled space + active-set correction
@@ -888,9 +932,9 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       prip = 0.0;
 #pragma unroll
       for (int r = 0; r < QP_ROWS; r++) {
-        yp[r] = sm[(QP_SM_W + r) * 32 + lane];
-        const double l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
-        const double Er = sqrt(sm[(QP_SM_RHO + r) * 32 + lane] * (c / rhobar) * (((eqmask >> r) & 1u) ? 1e-3 : 1.0));
+        yp[r] = sm[(QP_SM_W + r) * STR + lane];
+        const double l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
+        const double Er = sqrt(sm[(QP_SM_RHO + r) * STR + lane] * (c / rhobar) * (((eqmask >> r) & 1u) ? 1e-3 : 1.0));
         prip = fmax(prip, Er * fmax(fmax(l - Axp[r], Axp[r] - u), 0.0));
         nax = fmax(nax, Er * fabs(Axp[r]));
         ny = fmax(ny, fabs(c * yp[r] / Er));
@@ -904,8 +948,8 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       if (active && !verified) {
 #pragma unroll
         for (int r = 0; r < QP_ROWS; r++) {
-          const double l = sm[(QP_SM_L + r) * 32 + lane], u = sm[(QP_SM_U + r) * 32 + lane];
-          const double Er = sqrt(sm[(QP_SM_RHO + r) * 32 + lane] * (c / rhobar) * (((eqmask >> r) & 1u) ? 1e-3 : 1.0));
+          const double l = sm[(QP_SM_L + r) * STR + lane], u = sm[(QP_SM_U + r) * STR + lane];
+          const double Er = sqrt(sm[(QP_SM_RHO + r) * STR + lane] * (c / rhobar) * (((eqmask >> r) & 1u) ? 1e-3 : 1.0));
           const unsigned bit = 1u << r;
           if (!(actm & bit)) {
             if (Er * (l - Axp[r]) > tol_p) { lowm |= bit; changed = 1; }
@@ -924,7 +968,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
         if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
         apply_AT(yp, n18, n19, n20, t, tp, tn, first, aty);
       }
-      apply_P(sm, lane, xp, px);
+      apply_P<STR>(sm, lane, xp, px);
       duap = 0.0;
       double dscale = 0.0;
 #pragma unroll
@@ -958,7 +1002,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
   // ---------------- outputs ----------------
   {
     double px[6];
-    apply_P(sm, lane, x, px);
+    apply_P<STR>(sm, lane, x, px);
     double ob = 0.0;
 #pragma unroll
     for (int j = 0; j < 6; j++) ob += x[j] * (0.5 * px[j] + q[j]);
@@ -976,4 +1020,22 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
       a.axis_obj[2 * b + axis] = ob;
     }
   }
+}
+
+// One warp = 32/LPA axis problems (k_qp): setup, lane-per-segment ADMM, finish.
+template <int LPA, int JW>
+SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm) {
+  constexpr int G = 32 / LPA;
+  const int cnt = *a.count;
+  const int grp = lane / LPA, seg = lane % LPA;
+  const int ap = warp_global * G + grp;  // axis-problem slot in this class
+  if (warp_global * G >= 2 * cnt) return;
+  const bool have = ap < 2 * cnt;
+  QpLane Q;
+  qp_setup<LPA, 32, JW>(a, ap, have, seg, lane, sm, Q);
+  QpFactor F;
+  double x[6];
+  int state, iters;
+  qp_admm_lanes<LPA, 32, JW>(a.opt, sm, lane, Q, F, x, state, iters);
+  qp_finish<LPA, 32, JW>(a, sm, lane, Q, x, state, iters);
 }

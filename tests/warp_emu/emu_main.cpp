@@ -89,9 +89,9 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
     for (int w = 0; w < nw; w++) {
       std::vector<double> sm(QP_SM_DOUBLES_PER_LANE * 32);
       run_warps(1, [&](int, int l, pthread_barrier_t *) {
-        if (lpa == 8) qp_warp_body<8>(qa, w, l, sm.data());
-        else if (lpa == 16) qp_warp_body<16>(qa, w, l, sm.data());
-        else qp_warp_body<32>(qa, w, l, sm.data());
+        if (lpa == 8) qp_warp_body<8, 16>(qa, w, l, sm.data());
+        else if (lpa == 16) qp_warp_body<16, 32>(qa, w, l, sm.data());
+        else qp_warp_body<32, 32>(qa, w, l, sm.data());
       });
     }
   }

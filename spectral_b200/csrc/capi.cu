@@ -14,6 +14,7 @@
 #include "corridor.cuh"
 #include "finalize.cuh"
 #include "qp.cuh"
+#include "qp_dense.cuh"
 #include "tables.cuh"
 
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
@@ -36,17 +37,17 @@ __global__ void k_classify(const int *cstatus, const int *K, int B, int *lists, 
 // classification that keeps scenario order (one CTA, used for small batches so runs are reproducible
 // lane-for-lane; the atomic version above is used for large ones)
 __global__ void k_classify_ordered(const int *cstatus, const int *K, int B, int *lists, int *counts) {
-  __shared__ int base[3];
-  __shared__ int wsum[3][32];
-  if (threadIdx.x < 3) base[threadIdx.x] = 0;
+  __shared__ int base[SP_NUM_CLASSES];
+  __shared__ int wsum[SP_NUM_CLASSES][32];
+  if (threadIdx.x < SP_NUM_CLASSES) base[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int start = 0; start < B; start += blockDim.x) {
     const int b = start + threadIdx.x;
     int cls = -1;
     if (b < B && cstatus[b] == 0) cls = lane_class(K[b]);
-    int pos[3];
-    for (int c = 0; c < 3; c++) {
+    int pos[SP_NUM_CLASSES];
+    for (int c = 0; c < SP_NUM_CLASSES; c++) {
       const unsigned m = __ballot_sync(0xffffffffu, cls == c);
       pos[c] = __popc(m & ((1u << lane) - 1));
       if (lane == 0) wsum[c][warp] = __popc(m);
@@ -58,14 +59,14 @@ __global__ void k_classify_ordered(const int *cstatus, const int *K, int B, int 
       lists[(size_t)cls * B + off + pos[cls]] = b;
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < SP_NUM_CLASSES) {
       int tot = 0;
       for (int w = 0; w < nw; w++) tot += wsum[threadIdx.x][w];
       base[threadIdx.x] += tot;
     }
     __syncthreads();
   }
-  if (threadIdx.x < 3) counts[threadIdx.x] = base[threadIdx.x];
+  if (threadIdx.x < SP_NUM_CLASSES) counts[threadIdx.x] = base[threadIdx.x];
 }
 
 template <int LPA, int WPB>
@@ -73,6 +74,13 @@ __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   extern __shared__ double qp_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   qp_warp_body<LPA, (LPA < 32 ? 2 * LPA : LPA)>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
+}
+
+// dense-operator ADMM kernel (qp_dense.cuh): one CTA of 128 threads per scenario of this class
+template <int KC>
+__global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, (KC <= 10 ? 2 : 1)) k_qpd(const QpArgs a) {
+  extern __shared__ __align__(16) double qpd_smem[];
+  qpd_cta_body<KC>(a, blockIdx.x, threadIdx.x, qpd_smem, []() { __syncthreads(); });
 }
 
 // `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:
@@ -165,6 +173,8 @@ struct DevBuf {
 struct spectral_handle {
   int device = 0, max_batch = 0, n_max = 0, r_max = 0, k_max = 0, sm_count = 148;
   cudaStream_t stream = nullptr;  // used by the host-buffer entry point
+  cudaStream_t side[SP_NUM_CLASSES - 1] = {};  // the solver classes run concurrently (fork / join around the QP stage)
+  cudaEvent_t ev_fork = nullptr, ev_join[SP_NUM_CLASSES - 1] = {};
   std::string err;
   long long launches = 0;
   bool timing = false;
@@ -226,10 +236,13 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto &s : h->side) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (auto &e : h->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t B = (size_t)max_batch;
   CK(cudaMalloc(&h->cstatus, B * 4));
-  CK(cudaMalloc(&h->lists, 3 * B * 4));
-  CK(cudaMalloc(&h->counts, 16));
+  CK(cudaMalloc(&h->lists, SP_NUM_CLASSES * B * 4));
+  CK(cudaMalloc(&h->counts, 4 * SP_NUM_CLASSES));
   CK(cudaMalloc(&h->axis_status, 2 * B * 4));
   CK(cudaMalloc(&h->axis_iters, 2 * B * 4));
   CK(cudaMalloc(&h->axis_polished, 2 * B * 4));
@@ -256,6 +269,9 @@ extern "C" int spectral_destroy(spectral_handle_t *h) {
   for (auto &slot : h->ev)
     for (auto &e : slot) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
+  for (auto &s : h->side) if (s) cudaStreamDestroy(s);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto &e : h->ev_join) if (e) cudaEventDestroy(e);
   delete h;
   return SPECTRAL_SUCCESS;
 }
@@ -289,6 +305,16 @@ extern "C" int spectral_get_work(spectral_handle_t *h, double work[4], int reset
   CK(cudaMemcpy(work, h->work, 4 * 8, cudaMemcpyDeviceToHost));
   if (reset) CK(cudaMemset(h->work, 0, 4 * 8));
   return SPECTRAL_SUCCESS;
+}
+
+template <int KC>
+static cudaError_t launch_qpd(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
+  const size_t smem = QpdLayout<KC>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(k_qpd<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_qpd<KC><<<B, 2 * QpdLayout<KC>::TA, smem, st>>>(qa);
+  h->launches++;
+  return cudaGetLastError();
 }
 
 template <int LPA, int WPB>
@@ -336,7 +362,7 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // classification by segment count -> lane class lists
-  CK(cudaMemsetAsync(h->counts, 0, 16, st));
+  CK(cudaMemsetAsync(h->counts, 0, 4 * SP_NUM_CLASSES, st));
   if (B <= 4096) k_classify_ordered<<<1, 1024, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   else k_classify<<<(B + 255) / 256, 256, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   h->launches++;
@@ -355,15 +381,22 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   qa.opt.polish_delta = opt.polish_delta; qa.opt.polish_rounds = opt.polish_rounds;
   qa.ctrl = out->ctrl; qa.axis_status = h->axis_status; qa.axis_iters = h->axis_iters; qa.axis_polished = h->axis_polished;
   qa.axis_obj = h->axis_obj; qa.lu = out->lu;
-  qa.list = h->lists; qa.count = h->counts + 0;
-  CK((launch_qp<8, 2>(h, qa, B, st)));
-  if (h->k_max > 8) {
-    qa.list = h->lists + (size_t)B; qa.count = h->counts + 1;
-    CK((launch_qp<16, 2>(h, qa, B, st)));
-  }
-  if (h->k_max > 16) {
-    qa.list = h->lists + 2 * (size_t)B; qa.count = h->counts + 2;
-    CK((launch_qp<32, 2>(h, qa, B, st)));
+  // the solver classes are independent: fork them onto side streams, join before K5
+  CK(cudaEventRecord(h->ev_fork, st));
+  for (int cls = 0; cls < SP_NUM_CLASSES; cls++) {
+    if (cls > 0 && class_kcap(cls - 1) >= h->k_max) break;  // class cannot occur with this handle's k_max
+    cudaStream_t cs = cls == 0 ? st : h->side[cls - 1];
+    if (cls > 0) CK(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+    qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls;
+    if (cls == 0) CK((launch_qpd<8>(h, qa, B, cs)));
+    else if (cls == 1) CK((launch_qpd<10>(h, qa, B, cs)));
+    else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));
+    else if (cls == 3) CK((launch_qpd<16>(h, qa, B, cs)));
+    else CK((launch_qp<32, 2>(h, qa, B, cs)));
+    if (cls > 0) {
+      CK(cudaEventRecord(h->ev_join[cls - 1], cs));
+      CK(cudaStreamWaitEvent(st, h->ev_join[cls - 1], 0));
+    }
   }
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 

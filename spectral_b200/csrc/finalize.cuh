@@ -20,8 +20,12 @@ struct FinalArgs {
   int samples_cap;
 };
 
-// lane class of a scenario: 0 -> 8 lanes per axis problem, 1 -> 16, 2 -> 32
-SP_DEV int lane_class(int K) { return K <= 8 ? 0 : (K <= 16 ? 1 : 2); }
+// solver class of a scenario by segment count:
+//   0: K <= 8  k_qpd<8>   1: K <= 10  k_qpd<10>   2: K <= 12  k_qpd<12>   3: K <= 16  k_qpd<16>   (dense kernels)
+//   4: K <= 32  lane-per-segment k_qp<32>
+#define SP_NUM_CLASSES 5
+SP_DEV int lane_class(int K) { return K <= 8 ? 0 : (K <= 10 ? 1 : (K <= 12 ? 2 : (K <= 16 ? 3 : 4))); }
+SP_HD int class_kcap(int cls) { return cls == 0 ? 8 : (cls == 1 ? 10 : (cls == 2 ? 12 : (cls == 3 ? 16 : 32))); }
 
 SP_DEV void bernstein_powers(double u, double up[6], double vp[6]) {
   up[0] = 1.0; vp[0] = 1.0;

@@ -55,6 +55,40 @@ def test_emu_full_solve_c2_matches_converged_oracle():
     assert 0 < int(got.iters[0]) < 5000 and int(ref0["iters"][0]) < 5000
 
 
+def _subset(batch, idx):
+    idx = np.asarray(idx)
+    return ScenarioBatch(batch.n_knots, batch.n_regions, batch.delta_t, *[x[idx] for x in batch.arrays()])
+
+
+def test_emu_dense_kernel_tracks_reference_osqp():
+    """The dense-operator ADMM loop (qp_dense.cuh, k_qpd<8> and k_qpd<10>) solves both axes of a scenario as ONE
+    OSQP instance like the reference: on scenarios that converge quickly the ITERATION COUNT equals that of the
+    reference-settings oracle, infeasible ones are certified at the same check, and the polished control
+    points match the converged oracle.  Scenarios: K = 9 (#779), K = 10 (#508: 1200 iterations), an early
+    infeasible one (#914) and the K = 8 base (#0) of config 2."""
+    from spectral_b200.scenarios import GOLDEN_W_CUB
+    batch = _subset(config2(1024), [0, 779, 914])
+    got = H.emu_solve("cub", batch, GOLDEN_W_CUB)
+    ref, ref0 = H.oracle_pair("cub", batch, GOLDEN_W_CUB)
+    assert list(got.K) == [8, 9, 4]
+    assert np.array_equal(got.iters, ref0["iters"]), (got.iters, ref0["iters"])
+    assert np.array_equal(got.ok(), ref0["status"] <= 1)
+    H.assert_batch_parity(got, ref, "emu/dense", need_verified_frac=1.0, ref0=ref0)
+
+
+def test_emu_lane_kernel_matches_dense_kernel(monkeypatch):
+    """The lane-per-segment loop (qp.cuh, used above the dense kernel's capacity) and the dense loop are the
+    same OSQP iteration: same iteration count, same status, same polished optimum."""
+    batch = ScenarioBatch.from_scenarios([load_fixture("c4_2")])
+    dense = H.emu_solve("trp", batch, WEIGHTS_FILE)
+    monkeypatch.setenv("SPECTRAL_EMU_LANES", "1")
+    lanes = H.emu_solve("trp", batch, WEIGHTS_FILE)
+    assert dense.status[0] == lanes.status[0] == 0 and dense.iters[0] == lanes.iters[0]
+    assert dense.verified()[0] and lanes.verified()[0]
+    K = int(dense.K[0])
+    assert H.close(dense.ctrl[0, :12 * K], lanes.ctrl[0, :12 * K], rtol=1e-7, atol=1e-8)
+
+
 def test_emu_failure_classes():
     far = load_fixture("c1")
     far.l_ref = far.l_ref + 100.0

@@ -7,6 +7,7 @@
 #include "../../spectral_b200/csrc/common.cuh"
 #include "../../spectral_b200/csrc/corridor.cuh"
 #include "../../spectral_b200/csrc/qp.cuh"
+#include "../../spectral_b200/csrc/qp_dense.cuh"
 #include "../../spectral_b200/csrc/tables.cuh"
 #include "../../spectral_b200/csrc/finalize.cuh"
 
@@ -43,6 +44,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
                                const SpectralOptions *opt, int *K, SpectralCube *segs, double *ctrl,
                                double *obj, double *a_cost, int *status, int *iters, int *flags, int *npts,
                                double *samples, int samples_cap, double *lu) {
+  const bool force_lanes = getenv("SPECTRAL_EMU_LANES") != nullptr;  // run the lane-per-segment loop for every class
   std::vector<int> cstatus(B, 0);
   // ---- corridor kernel: one CTA per scenario, R warps
   CorridorArgs ca{B, N, R, variant, k_max, delta, s_bounds, l_bounds, s_ref, l_ref, segs, K, cstatus.data()};
@@ -63,7 +65,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
   for (int w = 0; w < W; w++)
     for (int ax = 0; ax < 2; ax++) mqm_body(weights, mqm.data(), w, ax);
   // ---- classification
-  std::vector<int> list[3];
+  std::vector<int> list[SP_NUM_CLASSES];
   for (int b = 0; b < B; b++)
     if (cstatus[b] == 0) list[lane_class(K[b])].push_back(b);
   // ---- QP kernel per lane class
@@ -74,7 +76,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
   od.adapt_every = opt->adaptive_rho_interval; od.polish = opt->polish; od.polish_refine = opt->polish_refine_iter;
   od.eps_abs = opt->eps_abs; od.eps_rel = opt->eps_rel; od.eps_pinf = opt->eps_prim_inf; od.rho0 = opt->rho;
   od.sigma = opt->sigma; od.alpha = opt->alpha; od.adapt_tol = opt->adaptive_rho_tolerance; od.polish_delta = opt->polish_delta; od.polish_rounds = opt->polish_rounds;
-  for (int cls = 0; cls < 3; cls++) {
+  for (int cls = 0; cls < SP_NUM_CLASSES; cls++) {
     int cnt = (int)list[cls].size();
     if (!cnt) continue;
     QpArgs qa;
@@ -83,7 +85,25 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
     qa.scalars = scalars; qa.weights = weights; qa.wstride = wstride; qa.mqm = mqm.data(); qa.segs = segs; qa.K = K;
     qa.list = list[cls].data(); qa.count = &cnt; qa.opt = od; qa.ctrl = ctrl; qa.axis_status = axis_status.data();
     qa.axis_iters = axis_iters.data(); qa.axis_polished = axis_pol.data(); qa.axis_obj = axis_obj.data(); qa.lu = lu;
-    const int lpa = cls == 0 ? 8 : (cls == 1 ? 16 : 32);
+    if (cls <= 3 && !force_lanes) {
+      // dense kernel: one CTA of 2 TA threads per scenario
+      const int total = cls == 0 ? QpdLayout<8>::TOTAL : cls == 1 ? QpdLayout<10>::TOTAL : cls == 2 ? QpdLayout<12>::TOTAL : QpdLayout<16>::TOTAL;
+      const int nwarps = cls <= 1 ? 4 : 6;
+      for (int slot = 0; slot < cnt; slot++) {
+        std::vector<double> sm(total + 2);
+        double *base = sm.data();
+        if ((uintptr_t)base & 15) base += 1;
+        run_warps(nwarps, [&](int w, int l, pthread_barrier_t *cta) {
+          auto sync = [cta]() { pthread_barrier_wait(cta); };
+          if (cls == 0) qpd_cta_body<8>(qa, slot, 32 * w + l, base, sync);
+          else if (cls == 1) qpd_cta_body<10>(qa, slot, 32 * w + l, base, sync);
+          else if (cls == 2) qpd_cta_body<12>(qa, slot, 32 * w + l, base, sync);
+          else qpd_cta_body<16>(qa, slot, 32 * w + l, base, sync);
+        });
+      }
+      continue;
+    }
+    const int lpa = cls <= 0 ? 8 : (cls <= 3 ? 16 : 32);
     const int G = 32 / lpa;
     const int nw = (2 * cnt + G - 1) / G;
     for (int w = 0; w < nw; w++) {

@@ -159,13 +159,13 @@ int spectral_measure_fp64_peak(spectral_handle_t *h, double *tflops);
  * kernel class of each solve_batch*_ call while timing is enabled.  Nothing synchronises inside the
  * calls; spectral_get_timing() waits for the recorded events and returns the SUM of milliseconds per
  * class over the last `*calls` (<= 64) calls since spectral_set_timing(h, 1). */
-#define SPECTRAL_NUM_KERNELS 6 /* tables, corridor, classify, qp, finalize, (argmin: not timed) */
+#define SPECTRAL_NUM_KERNELS 6 /* tables, corridor, classify, qp (all solver classes, forked streams), finalize, (argmin: not timed) */
 int spectral_set_timing(spectral_handle_t *h, int enabled);
 int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS], int *calls);
 
 /* Work counters accumulated on the device by every solve_batch*_ call (synchronises the device):
  * work[0] ADMM iterations summed over axis problems, work[1] their algorithmic flops
- * ((424 K - 168) per axis-iteration), work[2] scenarios processed, work[3] scenarios solved. */
+ * (72 K^2 + 208 K - 24 per axis-iteration: dense apply of the 6K x 6K inverse + A, A' products), work[2] scenarios processed, work[3] scenarios solved. */
 int spectral_get_work(spectral_handle_t *h, double work[4], int reset);
 
 /* The reference's plugin entry point (exported by libtrp.so / libcub.so, not by libspectral.so):

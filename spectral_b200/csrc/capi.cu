@@ -76,16 +76,19 @@ __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   qp_warp_body<LPA, (LPA < 32 ? 2 * LPA : LPA)>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
 }
 
-// dense-operator ADMM kernel (qp_dense.cuh): one CTA of 128 threads per scenario of this class
+// dense-operator ADMM kernel (qp_dense.cuh): one CTA (2 TA threads) per scenario of this class
+#ifndef QPD_MINBLOCKS
+#define QPD_MINBLOCKS(KC) ((KC) <= 10 ? 2 : 1)
+#endif
 template <int KC>
-__global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, (KC <= 10 ? 2 : 1)) k_qpd(const QpArgs a) {
+__global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, QPD_MINBLOCKS(KC)) k_qpd(const QpArgs a) {
   extern __shared__ __align__(16) double qpd_smem[];
   qpd_cta_body<KC>(a, blockIdx.x, threadIdx.x, qpd_smem, []() { __syncthreads(); });
 }
 
 // `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:
 //   work[0] += ADMM iterations summed over the axis problems of this batch
-//   work[1] += algorithmic flops of those iterations, (424 K - 168) per axis-iteration
+//   work[1] += algorithmic flops of those iterations, 72 K^2 + 208 K - 24 per axis-iteration
 //   work[2] += scenarios processed,  work[3] += scenarios solved
 __global__ void k_finalize(const FinalArgs a, double *work) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,7 +98,10 @@ __global__ void k_finalize(const FinalArgs a, double *work) {
     cnt = 1.0;
     if (a.cstatus[b] == 0) {
       it = (double)a.axis_iters[2 * b] + (double)a.axis_iters[2 * b + 1];
-      fl = it * (424.0 * a.K[b] - 168.0);
+      // algorithmic flops per axis-iteration: dense apply of the 6K x 6K inverse + A and A' products,
+      // 2 (6K)^2 + 4 (52K - 6); above the dense kernels' capacity the block-tridiagonal count 424 K - 168
+      const double Kd = (double)a.K[b];
+      fl = it * (a.K[b] <= 16 ? 72.0 * Kd * Kd + 208.0 * Kd - 24.0 : 424.0 * Kd - 168.0);
       const int s0 = a.axis_status[2 * b], s1 = a.axis_status[2 * b + 1];
       ok = ((s0 == QP_ST_SOLVED || s0 == QP_ST_INACCURATE) && (s1 == QP_ST_SOLVED || s1 == QP_ST_INACCURATE)) ? 1.0 : 0.0;
     }

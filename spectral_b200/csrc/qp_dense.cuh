@@ -10,17 +10,20 @@
 // at the batch sizes of BASELINE.json (ncu, profiles/r1_qp_lanes.md: 13 k cycles per iteration, FP64 pipe
 // 5 % busy).  Here the reduced KKT matrix S = P + sigma I + A' rho A of one axis (n = 6 KC <= 60) is inverted
 // ONCE per rho (setup and the rare adaptive-rho updates) and the inverse G = S^-1 is kept in REGISTERS, one
-// row per thread (n doubles), so the per-iteration solve x~ = G g is n independent FMAs per thread with the
+// row per thread pair (n/2 doubles each), so the per-iteration solve x~ = G g is n/2 independent FMAs per thread with the
 // right-hand side broadcast from shared memory: no dependent chain, no shuffles.  A and A' are never stored:
 // their rows are finite-difference stencils of the control points (solve_3d.cc:823-949), applied from
 // zero-padded shared-memory arrays so that every thread runs the same instruction stream.
 //
-// Thread map (TA = 64 threads per axis for KC <= 10, 96 above; CTA = 2 TA):
-//   variable thread v < n         : row v of G, relaxed iterate x_v, gathers (A' v)_v, computes x~_v
-//   row slots e = ta + TA s < 21KC: w_e = z_e + y_e / rho_e, l_e, u_e, rho_e in registers; rows are ordered by
-//                                   type [containment | velocity | acceleration | jerk | continuity/init]
+// Thread map (per axis TA = 2n threads rounded up to whole warps: 96 for KC = 8; CTA = 2 TA):
+//   thread (v, h) = ta >> 1, ta & 1 : half row h of G (n/2 doubles in registers); the h = 0 thread also owns the
+//                                     relaxed iterate x_v, gathers (A' v)_v and publishes x~_v
+//   row slots                       : every thread owns up to two "difference" rows (containment, velocity,
+//                                     acceleration, jerk: one code path, the order of the finite difference is
+//                                     selected per row) or one difference row and one continuity/init row; their
+//                                     w = z + y / rho, clip(w), l, u, rho live in registers
 // Per iteration (3 CTA barriers):  S2 gather g = A'(rho (2 clip(w) - w)) + sigma x - q   (13 LDS + 16 FMA)
-//                                  S3 x~ = G g, x = alpha x~ + (1 - alpha) x              (n FMA)
+//                                  S3 x~ = G g: n/2 FMAs per thread + one shuffle, x = alpha x~ + (1 - alpha) x
 //                                  S1 z~ = A x~ (stencil), w += alpha (z~ - clip(w)), next v   (per row slot)
 // Every check_termination iterations the residual / infeasibility norms of OSQP are evaluated in the same
 // layout (CTA-wide reductions); adaptive-rho updates re-run the factorisation of qp.cuh on warp 0 and
@@ -30,24 +33,31 @@
 #include "common.cuh"
 #include "qp.cuh"
 
-#define QPD_VB 33         // doubles per segment block of the padded row-value array V
+#define QPD_VB 38         // doubles per segment block of the padded row-value array V (38 = 6 mod 16: the gather of
+                          // variable v = 6k + j hits bank pair v mod 16, conflict free)
 #define QPD_V0 0          // containment rows      V0[i], i = 0..5
 #define QPD_V1 7          // velocity rows         V1[i] at 7 + i,  i = -1..5 (pads at 6, 12)
 #define QPD_V2 15         // acceleration rows     V2[i] at 15 + i, i = -2..5 (pads at 13, 14, 19, 20)
 #define QPD_V3 24         // jerk rows             V3[i] at 24 + i, i = -3..5 (pads at 21..23, 27..29)
 #define QPD_VC 30         // continuity/init rows  Vc[r] at 30 + r
+#define QPD_CP 3          // leading pads of the control-point arrays C / XR (window of the first continuity rows)
 #define QPD_LS 24         // doubles of lane state per segment: t, tp, tn, q[6], sig[6], cD[6]
 #define QPD_NRED 10
 
-enum { QPD_T_CONT = 0, QPD_T_VEL = 1, QPD_T_ACC = 2, QPD_T_JERK = 3, QPD_T_JOIN = 4 };
-
 template <int KC>
 struct QpdLayout {
+  static_assert(KC % 2 == 0, "the two half rows of G split the segments evenly");
   static constexpr int N = 6 * KC;             // variables per axis
+  static constexpr int CH = N / 2;             // columns of G per thread
+  static constexpr int KB = KC / 2;            // segments per half row
   static constexpr int ROWS = 21 * KC;         // constraint rows per axis
-  static constexpr int TA = ((N + 31) / 32) * 32;          // threads per axis problem (64 for KC <= 10, 96 above)
-  static constexpr int NWARPS = 2 * TA / 32;               // warps per CTA
-  static constexpr int NS = (ROWS + TA - 1) / TA;          // row slots per thread
+  static constexpr int NN = 18 * KC;           // difference rows (containment, velocity, acceleration, jerk)
+  static constexpr int NJ = 3 * KC;            // continuity / initial-state rows
+  static constexpr int TA = ((2 * N + 31) / 32) * 32;  // threads per axis problem
+  static constexpr int NWARPS = 2 * TA / 32;           // warps per CTA
+  static constexpr int T0 = ((NJ + 31) / 32) * 32;     // first thread without a continuity row
+  static constexpr int TN = TA - T0;                   // threads that own two difference rows
+  static_assert(2 * TN + T0 >= NN, "row slots");
   static constexpr int LPA = KC <= 8 ? 8 : 16; // lanes per axis of the lane-per-segment (control) code
   static constexpr int STR = LPA;              // its shared-memory stride
   // per-axis shared memory (doubles)
@@ -55,13 +65,13 @@ struct QpdLayout {
   static constexpr int O_FS = O_CTRL + QP_SM_DOUBLES_PER_LANE * STR; // factor store [LPA][57]
   static constexpr int O_LS = O_FS + 57 * LPA;                       // lane state [LPA][QPD_LS]
   static constexpr int O_V = O_LS + QPD_LS * LPA;                    // V[(KC+1)][QPD_VB]
-  static constexpr int O_GV = O_V + QPD_VB * (KC + 1) + 1;           // g[N]  (16-byte aligned below)
-  static constexpr int O_C = O_GV + N + (N & 1);                     // x~: 3 pad + N (+ pad)
-  static constexpr int O_XR = O_C + N + 4;                           // relaxed x for the checks: 3 pad + N
-  static constexpr int O_CE = O_XR + N + 4;                          // continuity row coefficients [3KC][6]
+  static constexpr int O_GV = O_V + QPD_VB * (KC + 1);               // g[N]  (even offset: 16-byte aligned)
+  static constexpr int O_C = O_GV + N;                               // x~: QPD_CP pads + N + pads
+  static constexpr int O_XR = O_C + N + 8;                           // relaxed x for the checks, same shape
+  static constexpr int O_CE = O_XR + N + 8;                          // continuity row coefficients [3KC][6]
   static constexpr int O_VCF = O_CE + 18 * KC;                       // continuity gather coefficients [N][3]
-  static constexpr int O_TK = O_VCF + 3 * N;                         // segment durations [KC]
-  static constexpr int AXIS = ((O_TK + KC + 1) / 2) * 2;             // doubles per axis (even)
+  static constexpr int O_LU = ((O_VCF + 3 * N + 1) / 2) * 2;         // (l, u) of the row slots [3][TA] pairs (16-byte aligned)
+  static constexpr int AXIS = O_LU + 6 * TA;                         // doubles per axis (even)
   // per-CTA tail: reduction scratch [NWARPS][QPD_NRED], eqmask ints [2][LPA]
   static constexpr int O_RED = 2 * AXIS;
   static constexpr int O_EQ = O_RED + NWARPS * QPD_NRED;
@@ -72,7 +82,11 @@ struct QpdLayout {
   static constexpr int BYTES = TOTAL * 8;
 };
 
-SP_DEV double qpd_clip(double w, double l, double u) { return fmin(fmax(w, l), u); }
+// clip(w, [l, u]) as two compare-selects (fmin/fmax expand to NaN-propagation sequences four times as long)
+SP_DEV double qpd_clip(double w, double l, double u) {
+  const double a = w < l ? l : w;
+  return a > u ? u : a;
+}
 
 // (A' V)_v for variable (k, j): vb = V block of segment k, vk = V block holding the continuity rows that
 // touch this variable (own segment for j < 3, next segment for j >= 3), vc = their three coefficients
@@ -86,53 +100,79 @@ SP_DEV double qpd_gather(const double *vb, const double *vk, int j, double tk, d
   return g;
 }
 
-// (A c)_e for a row of the given type; cp points at c[k][i] (continuity rows: at c[k-1][3]), ce = its 6 coefficients
-SP_DEV double qpd_row(int type, const double *cp, double tk, const double *ce) {
-  if (type == QPD_T_CONT) return tk * cp[0];
-  if (type == QPD_T_VEL) return 5.0 * (cp[1] - cp[0]);
-  if (type == QPD_T_ACC) return 20.0 * ((cp[2] - cp[1]) - (cp[1] - cp[0]));
-  if (type == QPD_T_JERK) return 60.0 * (((cp[3] - cp[2]) - (cp[2] - cp[1])) - ((cp[2] - cp[1]) - (cp[1] - cp[0])));
-  return ce[0] * cp[0] + ce[1] * cp[1] + ce[2] * cp[2] + ce[3] * cp[3] + ce[4] * cp[4] + ce[5] * cp[5];
+// difference rows: order-d finite difference of the control points at cp, d = 0..3 (solve_3d.cc:823-888):
+//   containment t c_i | velocity 5 (c_{i+1} - c_i) | acceleration 20 (c_i - 2 c_{i+1} + c_{i+2}) | jerk 60 (...)
+// One code path for all four: the window cp[0..3] is always read (the arrays are padded), the order selects.
+SP_DEV double qpd_diff_row(const double *cp, int order, double scale) {
+  const double c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
+  const double d1 = c1 - c0, e1 = c2 - c1, f1 = c3 - c2;
+  const double d2 = e1 - d1, e2 = f1 - e1;
+  const double d3 = e2 - d2;
+  const double lo = order == 0 ? c0 : d1, hi = order == 2 ? d2 : d3;
+  return scale * (order < 2 ? lo : hi);
+}
+// continuity / initial-state rows (solve_3d.cc:896-949): six coefficients on [c_{k-1,3..5}, c_{k,0..2}]
+SP_DEV double qpd_join_row(const double *cp, const double *ce) {
+  return (ce[0] * cp[0] + ce[1] * cp[1]) + (ce[2] * cp[2] + ce[3] * cp[3]) + (ce[4] * cp[4] + ce[5] * cp[5]);
 }
 
-template <int KC>
-struct QpdRowSlot {
-  double w, l, u, rho;
-  int coff;   // offset of the first control point of the stencil in C / XR
-  int voff;   // offset of this row's value in V
-  int ooff;   // offset of this row in the lane-per-segment slots (r * STR + k), add QP_SM_* * STR
-  int meta;   // bits 0-2 type, bit 3 valid, bit 4 equality row, bits 8.. segment, bits 16.. row index in type
+struct QpdLU { double l, u; };
+struct QpdRow {
+  double w, p, rho;        // w = z + y / rho, p = clip(w, l, u); (l, u) live in shared memory (QpdLayout::O_LU)
+  double scale;            // difference rows: t_k, 5, 20 or 60
+  int coff;                // offset of the stencil window in C / XR
+  int voff;                // offset of this row's value in V
+  int meta;                // bits 0-1 difference order, bit 3 valid, bit 4 equality row, bits 8-15 segment, 16.. row in slots (r)
 };
 
-// in-place solve S x = e_v with the block factor of qp.cuh read from shared memory (broadcast loads):
-// on return g[] holds row v of G = S^-1
+// Half row h of G = S^-1 for variable v: the thread pair (v, 0), (v, 1) runs the block forward / backward
+// substitution of qp.cuh's factor (read from shared memory, broadcast) on e_v, each on its own half of
+// the segments, handing the 3-value carry to the partner lane by shuffle.
 template <int KC>
-SP_DEV void qpd_inverse_row(const double *fs, int v, double *g) {
+SP_DEV void qpd_inverse_half_row(const double *fs, int v, int h, double *g) {
+  constexpr int KB = KC / 2;
   const int kv = v / 6, iv = v - 6 * kv;
-  // forward: y_k = Linv_k e_k - C_k y_{k-1}[3..5]
+  const int kbase = h * KB;
+  double c3 = 0.0, c4 = 0.0, c5 = 0.0;  // y_{k-1}[3..5]
 #pragma unroll
-  for (int k = 0; k < KC; k++) {
-    const double *F = fs + 57 * k;
+  for (int phase = 0; phase < 2; phase++) {
+    if (h == phase) {
 #pragma unroll
-    for (int a = 0; a < 6; a++) {
-      double y = 0.0;
-      if (k == kv && a >= iv) y = F[LT(a, 0) + iv];
-      if (k > 0) y -= F[21 + a * 3 + 0] * g[6 * (k - 1) + 3] + F[21 + a * 3 + 1] * g[6 * (k - 1) + 4] + F[21 + a * 3 + 2] * g[6 * (k - 1) + 5];
-      g[6 * k + a] = y;
+      for (int kb = 0; kb < KB; kb++) {
+        const int k = kbase + kb;
+        const double *F = fs + 57 * k;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          double y = 0.0;
+          if (k == kv && a >= iv) y = F[LT(a, 0) + iv];
+          y -= F[21 + a * 3 + 0] * c3 + F[21 + a * 3 + 1] * c4 + F[21 + a * 3 + 2] * c5;  // C_0 = 0
+          g[6 * kb + a] = y;
+        }
+        c3 = g[6 * kb + 3]; c4 = g[6 * kb + 4]; c5 = g[6 * kb + 5];
+      }
     }
+    if (phase == 0) { c3 = sp_shfl_xor(c3, 1); c4 = sp_shfl_xor(c4, 1); c5 = sp_shfl_xor(c5, 1); }
   }
-  // backward: x_k = Linv_k' y_k - E_k x_{k+1}[0..2]
+  double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // x_{k+1}[0..2]
 #pragma unroll
-  for (int k = KC - 1; k >= 0; k--) {
-    const double *F = fs + 57 * k;
+  for (int phase = 1; phase >= 0; phase--) {
+    if (h == phase) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      double x = 0.0;
+      for (int kb = KB - 1; kb >= 0; kb--) {
+        const int k = kbase + kb;
+        const double *F = fs + 57 * k;
 #pragma unroll
-      for (int a = i; a < 6; a++) x += F[LT(a, i)] * g[6 * k + a];
-      if (k < KC - 1) x -= F[39 + i * 3 + 0] * g[6 * (k + 1) + 0] + F[39 + i * 3 + 1] * g[6 * (k + 1) + 1] + F[39 + i * 3 + 2] * g[6 * (k + 1) + 2];
-      g[6 * k + i] = x;
+        for (int i = 0; i < 6; i++) {
+          double x = 0.0;
+#pragma unroll
+          for (int a = i; a < 6; a++) x += F[LT(a, i)] * g[6 * kb + a];
+          x -= F[39 + i * 3 + 0] * n0 + F[39 + i * 3 + 1] * n1 + F[39 + i * 3 + 2] * n2;  // E of the last segment = 0
+          g[6 * kb + i] = x;
+        }
+        n0 = g[6 * kb + 0]; n1 = g[6 * kb + 1]; n2 = g[6 * kb + 2];
+      }
     }
+    if (phase == 1) { n0 = sp_shfl_xor(n0, 1); n1 = sp_shfl_xor(n1, 1); n2 = sp_shfl_xor(n2, 1); }
   }
 }
 
@@ -217,7 +257,7 @@ SP_DEV_NOINLINE void qpd_control_setup(const QpArgs &a, int slot, int lane, doub
     qp_setup<LPA, STR, JW>(a, cap, creal, cseg, cseg, smc, Q);
     if (creal) qpd_store_lane(Q, cls, ceq);
     if (creal && cseg < KC) {
-      // stencil tables of the dense loop: continuity row coefficients, gather coefficients, durations
+      // stencil tables of the dense loop: continuity row coefficients, continuity gather coefficients
       double *ce = smem + caxis * L::AXIS + L::O_CE + 18 * cseg;
       double *vcf = smem + caxis * L::AXIS + L::O_VCF + 18 * cseg;
 #pragma unroll
@@ -229,7 +269,6 @@ SP_DEV_NOINLINE void qpd_control_setup(const QpArgs &a, int slot, int lane, doub
           vcf[3 * j + r] = Q.active ? row_coef(18 + r, j, Q.t, Q.tp, Q.first) : 0.0;                          // own rows, j < 3
           vcf[3 * (3 + j) + r] = (Q.active && !Q.last) ? prev_coef(18 + r, j, Q.tn, Q.t, false) : 0.0;       // next segment's rows
         }
-      smem[caxis * L::AXIS + L::O_TK + cseg] = Q.active ? Q.t : 0.0;
     }
     const int bad = qpd_refactor<KC>(smc, cfs, Q, creal);
     if (bad) state = QP_ST_INFEASIBLE;
@@ -277,246 +316,370 @@ SP_DEV_NOINLINE void qpd_control_finish(const QpArgs &a, int slot, int lane, dou
   QpLane Q;
   qpd_load_lane(Q, a, cap, cseg, cls, ceq, c_scale, rhobar, creal);
   double x[6];
-  const double *xs = smem + caxis * L::AXIS + L::O_XR + 3 + 6 * (cseg < KC ? cseg : 0);
+  const double *xs = smem + caxis * L::AXIS + L::O_XR + QPD_CP + 6 * (cseg < KC ? cseg : 0);
 #pragma unroll
   for (int j = 0; j < 6; j++) x[j] = (creal && cseg < KC) ? xs[j] : 0.0;
   qp_finish<LPA, STR, JW>(a, smc, cseg, Q, x, creal ? state : QP_ST_MAXITER, iters);
 }
 
 // ------------------------------------------------------------------ the CTA body
+// decode a difference-row index e in [0, 18 KC): order (0 containment .. 3 jerk), segment k, index i
+template <int KC>
+SP_DEV void qpd_decode_diff(int e, int &order, int &k, int &i) {
+  if (e < 6 * KC) { order = 0; k = e / 6; i = e - 6 * k; }
+  else if (e < 11 * KC) { order = 1; k = (e - 6 * KC) / 5; i = (e - 6 * KC) - 5 * k; }
+  else if (e < 15 * KC) { order = 2; k = (e - 11 * KC) / 4; i = (e - 11 * KC) - 4 * k; }
+  else { order = 3; k = (e - 15 * KC) / 3; i = (e - 15 * KC) - 3 * k; }
+}
+
+template <int KC>
+SP_DEV_NOINLINE void qpd_build_g(const double *fs, int v, int h, bool isg, double *out) {
+  double g[QpdLayout<KC>::CH];
+  qpd_inverse_half_row<KC>(fs, v, h, g);
+#pragma unroll
+  for (int e = 0; e < QpdLayout<KC>::CH; e++) out[e] = isg ? g[e] : 0.0;
+}
+
+// initial state of a difference-row slot: e = row index in [0, 18 KC) or < 0 (no row)
+template <int KC>
+SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl, const double *lsx, const int *eqa) {
+  using L = QpdLayout<KC>;
+  constexpr int STR = L::STR;
+  int order = 0, k = 0, i = 0;
+  const bool valid = e >= 0 && e < L::NN;
+  if (valid) qpd_decode_diff<KC>(e, order, k, i);
+  const int r_old = (order == 0 ? 0 : order == 1 ? 6 : order == 2 ? 11 : 15) + i;
+  const int vbase = order == 0 ? QPD_V0 : order == 1 ? QPD_V1 : order == 2 ? QPD_V2 : QPD_V3;
+  const bool live = valid && k < K;  // rows of unused segments stay inert: rho = 0, v = 0
+  const int ooff = r_old * STR + k;
+  const int eq = live ? ((eqa[k] >> r_old) & 1) : 0;
+  r.coff = QPD_CP + 6 * k + i;
+  r.voff = QPD_VB * k + vbase + i;
+  r.meta = order | (valid ? 8 : 0) | (eq ? 16 : 0) | (k << 8) | (r_old << 16);
+  r.scale = order == 0 ? (live ? lsx[QPD_LS * k] : 0.0) : (order == 1 ? 5.0 : (order == 2 ? 20.0 : 60.0));
+  r.w = 0.0; r.p = 0.0;
+  lu.l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
+  lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
+  r.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
+}
+
+// check iterations: delta y of a row -> V, its scaled norm (red_v[7]) and the support-function term (red_v[9])
+SP_DEV void qpd_check_dy(const QpdRow &r, const QpdLU &b, double yo, double *vv, double c_scale, double c_over_rhobar, double *red_v) {
+  if (!(r.meta & 8)) return;
+  const double dy = r.rho * (r.w - r.p) - yo;
+  vv[r.voff] = dy;
+  if (r.rho > 0.0) {
+    const double Er = sqrt(r.rho * c_over_rhobar * ((r.meta & 16) ? 1e-3 : 1.0));
+    red_v[7] = fmax(red_v[7], fabs(c_scale * dy / Er));
+    red_v[9] += c_scale * (b.u * fmax(dy, 0.0) + b.l * fmin(dy, 0.0));
+  }
+}
+// check iterations: primal residual terms of a row, ax = (A x)_row
+SP_DEV void qpd_check_resid(const QpdRow &r, double ax, double c_over_rhobar, double *red_v) {
+  if (!(r.meta & 8) || !(r.rho > 0.0)) return;
+  const double Er = sqrt(r.rho * c_over_rhobar * ((r.meta & 16) ? 1e-3 : 1.0));
+  red_v[0] = fmax(red_v[0], Er * fabs(ax - r.p));
+  red_v[2] = fmax(red_v[2], Er * fabs(r.p));
+  red_v[3] = fmax(red_v[3], Er * fabs(ax));
+}
+// adaptive rho: keep (z, y), w' = z + y / rho'; publish the new rho in the lane-per-segment RHO slots
+SP_DEV void qpd_rescale_row(QpdRow &r, double ratio, int K, double *ctl_rho, int str) {
+  if (!(r.meta & 8)) return;
+  r.w = r.p + (r.w - r.p) / ratio;
+  r.rho *= ratio;
+  const int k = (r.meta >> 8) & 0xff;
+  if (k < K) ctl_rho[(r.meta >> 16) * str + k] = r.rho;
+}
+SP_DEV void qpd_handback_row(const QpdRow &r, int K, double *ctl, int str) {
+  const int k = (r.meta >> 8) & 0xff;
+  if (!(r.meta & 8) || k >= K) return;
+  const int ooff = (r.meta >> 16) * str + k;
+  ctl[QP_SM_W * str + ooff] = r.w;
+  ctl[QP_SM_RHO * str + ooff] = r.rho;
+}
+
+// one ADMM row update: w += alpha (z~ - clip(w)); returns v = rho (2 clip(w) - w) of the new w
+SP_DEV double qpd_row_update(QpdRow &r, const QpdLU &b, double zt, double alpha) {
+  const double wn = r.w + alpha * (zt - r.p);
+  const double pn = qpd_clip(wn, b.l, b.u);
+  r.w = wn; r.p = pn;
+  return r.rho * (2.0 * pn - wn);
+}
+
+// Everything a check iteration needs from the hot loop, passed through local memory (the call is out of
+// line so that its register needs do not weigh on the loop).
+struct QpdCheckIO {
+  QpdRow rows[3];   // in: the thread's row slots; out: w and rho (adaptive rho rescales them)
+  double yo[3];     // multipliers before this iteration's update
+  double xv, qv, tkv, c_scale, rhobar;
+  int state, need_g, it;
+};
+
+// OSQP's termination test (residuals in the scaled space, scaled_termination = 1), primal-infeasibility
+// certificate and adaptive-rho rule, evaluated CTA-wide = jointly over the s and l problems of the scenario.
+// Called by all threads of the CTA on check iterations.
+template <int KC, typename SyncFn>
+SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem, QpdCheckIO &io, SyncFn sync_cta) {
+  using L = QpdLayout<KC>;
+  constexpr int N = L::N, LPA = L::LPA, STR = L::STR, TA = L::TA;
+  (void)LPA;
+  const SpOptionsDev &o = a.opt;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int axis = tid / TA, ta = tid - axis * TA;
+  double *smx = smem + axis * L::AXIS;
+  double *red = smem + L::O_RED;
+  const int K = a.K[a.list[slot]];
+  const double *ctl = smx + L::O_CTRL;
+  const double *lsx = smx + L::O_LS;
+  const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
+  const double *cej = smx + L::O_CE + 6 * (ta < L::NJ ? ta : 0);
+  const int v = ta >> 1, h = ta & 1;
+  const bool isg = v < N;
+  const bool isvar = isg && h == 0;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
+  const double *vb = smx + L::O_V + QPD_VB * vk;
+  const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
+  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);
+  double *xr = smx + L::O_XR;
+  double *vv = smx + L::O_V;
+  QpdRow &ra = io.rows[0], &rb = io.rows[1], &rj = io.rows[2];
+  const double c_scale = io.c_scale, xv = io.xv, qv = io.qv, tkv = io.tkv;
+  double rhobar = io.rhobar;
+  int state = io.state;
+  const int it = io.it;
+
+  double red_v[QPD_NRED];
+#pragma unroll
+  for (int i = 0; i < QPD_NRED; i++) red_v[i] = 0.0;
+  const double c_over_rhobar = c_scale / rhobar;
+  // delta y of this iteration -> V (for A' delta y), its norm and the support-function term of the certificate
+  qpd_check_dy(ra, lua[0], io.yo[0], vv, c_scale, c_over_rhobar, red_v);
+  qpd_check_dy(rb, lub[0], io.yo[1], vv, c_scale, c_over_rhobar, red_v);
+  qpd_check_dy(rj, luj[0], io.yo[2], vv, c_scale, c_over_rhobar, red_v);
+  sync_cta();
+  double cDv = 0.0;
+  if (isvar) {
+    if (vk < K) cDv = lsx[QPD_LS * vk + 15 + vj];
+    const double atd = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
+    red_v[8] = fabs(cDv * atd);
+    xr[QPD_CP + v] = xv;
+  }
+  sync_cta();
+  if (ra.meta & 8) vv[ra.voff] = ra.rho * (ra.w - ra.p);  // y
+  if (rb.meta & 8) vv[rb.voff] = rb.rho * (rb.w - rb.p);
+  if (rj.meta & 8) vv[rj.voff] = rj.rho * (rj.w - rj.p);
+  sync_cta();
+  if (isvar) {
+    const double aty = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
+    double px = 0.0;
+    const double *pk = ctl + QP_SM_P * STR + vk;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int e = (i >= vj) ? LT(i, vj) : LT(vj, i);
+      px += pk[e * STR] * xr[QPD_CP + 6 * vk + i];
+    }
+    if (vk >= K) px = 0.0;
+    red_v[1] = cDv * fabs(px + qv + aty);
+    red_v[4] = cDv * fabs(qv);
+    red_v[5] = cDv * fabs(px);
+    red_v[6] = cDv * fabs(aty);
+  }
+  qpd_check_resid(ra, qpd_diff_row(xr + ra.coff, ra.meta & 3, ra.scale), c_over_rhobar, red_v);
+  qpd_check_resid(rb, qpd_diff_row(xr + rb.coff, rb.meta & 3, rb.scale), c_over_rhobar, red_v);
+  qpd_check_resid(rj, qpd_join_row(xr + rj.coff, cej), c_over_rhobar, red_v);
+  qpd_reduce(red_v, red, warp, lane, L::NWARPS, sync_cta);
+  const double pri = red_v[0], dua = red_v[1], nz = red_v[2], nax = red_v[3], nq = red_v[4], npx = red_v[5], naty = red_v[6];
+  const double nd = red_v[7], na = red_v[8], lhs = red_v[9];
+  const double eps_p = o.eps_abs + o.eps_rel * fmax(nz, nax);
+  const double eps_d = o.eps_abs + o.eps_rel * fmax(nq, fmax(npx, naty));
+  if (pri < eps_p && dua < eps_d) state = QP_ST_SOLVED;
+  else if (!(pri < eps_p) && nd > o.eps_pinf && lhs < -o.eps_pinf * nd && na < o.eps_pinf * nd) state = QP_ST_INFEASIBLE;
+  // adaptive rho (OSQP's rule, every adaptive_rho_interval iterations)
+  if (state == QP_RUNNING && o.adapt_every > 0 && (it % o.adapt_every == 0)) {
+    const double pr = pri / (fmax(nz, nax) + 1e-10);
+    const double dr = dua / (fmax(nq, fmax(npx, naty)) + 1e-10);
+    double est = rhobar * sqrt(pr / (dr + 1e-10));
+    est = fmin(fmax(est, 1e-6), 1e6);
+    if (est > rhobar * o.adapt_tol || est < rhobar / o.adapt_tol) {
+      const double ratio = est / rhobar;
+      double *ctlw = smx + L::O_CTRL;
+      qpd_rescale_row(ra, ratio, K, ctlw + QP_SM_RHO * STR, STR);
+      qpd_rescale_row(rb, ratio, K, ctlw + QP_SM_RHO * STR, STR);
+      qpd_rescale_row(rj, ratio, K, ctlw + QP_SM_RHO * STR, STR);
+      rhobar = est;
+      sync_cta();
+      if (warp == 0) qpd_control_refactor<KC>(a, slot, lane, smem, c_scale, rhobar);
+      sync_cta();
+      if (red[0] != 0.0) state = QP_ST_INFEASIBLE;
+      io.need_g = 1;
+    }
+  }
+  io.rhobar = rhobar;
+  io.state = state;
+}
+
 // slot: index of the scenario in this class' list.  tid in [0, 2 TA).  smem: QpdLayout<KC>::BYTES, 16-byte aligned.
 template <int KC, typename SyncFn>
 SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
-  constexpr int N = L::N, ROWS = L::ROWS, NS = L::NS, LPA = L::LPA, STR = L::STR, JW = 2 * L::LPA, QPD_TA = L::TA;
-  (void)LPA; (void)JW;
+  constexpr int N = L::N, CH = L::CH, LPA = L::LPA, STR = L::STR, TA = L::TA;
   if (slot >= *a.count) return;
   const SpOptionsDev &o = a.opt;
   const int warp = tid >> 5, lane = tid & 31;
-  const int axis = tid / QPD_TA, ta = tid - axis * QPD_TA;
+  const int axis = tid / TA, ta = tid - axis * TA;
   double *smx = smem + axis * L::AXIS;  // this thread's axis region (fast layout)
   double *red = smem + L::O_RED;
-  int *eqm = (int *)(smem + L::O_EQ);
+  const int *eqm = (const int *)(smem + L::O_EQ);
   const int b = a.list[slot];
   const int K = a.K[b];
 
+  // ---------------- setup on warp 0: K3 assembly, Ruiz scaling, rho, first factorisation ----------------
   // (warp 0 doubles as the control warp: adjacent lane groups hold the s-axis and the l-axis problem in the
   // lane-per-segment layout of qp.cuh, see qpd_control_*)
-  // ---------------- setup on warp 0: K3 assembly, Ruiz scaling, rho, first factorisation ----------------
   double c_scale = 1.0, rhobar = o.rho0;
   int state = QP_RUNNING;
   if (warp == 0) qpd_control_setup<KC>(a, slot, lane, smem);
-  // zero the padded arrays of the fast layout (V incl. pads and the extra block, C / XR pads)
-  for (int i = ta; i < QPD_VB * (KC + 1) + 1; i += QPD_TA) smx[L::O_V + i] = 0.0;
-  for (int i = ta; i < N + 4; i += QPD_TA) { smx[L::O_C + i] = 0.0; smx[L::O_XR + i] = 0.0; }
+  // zero the padded arrays of the fast layout (V incl. pads and the extra block, C / XR incl. pads)
+  for (int i = ta; i < QPD_VB * (KC + 1); i += TA) smx[L::O_V + i] = 0.0;
+  for (int i = ta; i < N + 8; i += TA) { smx[L::O_C + i] = 0.0; smx[L::O_XR + i] = 0.0; }
   sync_cta();
   c_scale = red[0];
   state = (int)red[1];
   sync_cta();
 
   // ---------------- fast-layout state ----------------
-  QpdRowSlot<KC> rs[NS];
-#pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int e = ta + QPD_TA * s;
-    int type, k, i;
-    if (e < 6 * KC) { type = QPD_T_CONT; k = e / 6; i = e - 6 * k; }
-    else if (e < 11 * KC) { type = QPD_T_VEL; k = (e - 6 * KC) / 5; i = (e - 6 * KC) - 5 * k; }
-    else if (e < 15 * KC) { type = QPD_T_ACC; k = (e - 11 * KC) / 4; i = (e - 11 * KC) - 4 * k; }
-    else if (e < 18 * KC) { type = QPD_T_JERK; k = (e - 15 * KC) / 3; i = (e - 15 * KC) - 3 * k; }
-    else { type = QPD_T_JOIN; k = (e - 18 * KC) / 3; i = (e - 18 * KC) - 3 * k; }
-    const bool valid = e < ROWS;
-    if (!valid) { type = QPD_T_CONT; k = 0; i = 0; }
-    const int r_old = (type == QPD_T_CONT ? 0 : type == QPD_T_VEL ? 6 : type == QPD_T_ACC ? 11 : type == QPD_T_JERK ? 15 : 18) + i;
-    const int vbase = type == QPD_T_CONT ? QPD_V0 : type == QPD_T_VEL ? QPD_V1 : type == QPD_T_ACC ? QPD_V2 : type == QPD_T_JERK ? QPD_V3 : QPD_VC;
-    rs[s].coff = type == QPD_T_JOIN ? 6 * k : 3 + 6 * k + i;
-    rs[s].voff = QPD_VB * k + vbase + i;
-    rs[s].ooff = r_old * STR + k;
-    const bool live = valid && k < K;  // rows of unused segments stay inert: rho = 0, v = 0
+  const double *ctl = smx + L::O_CTRL;
+  const double *lsx = smx + L::O_LS;
+  QpdRow ra, rb, rj;  // two difference-row slots and the continuity-row slot of this thread
+  QpdLU *lua = (QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;  // their bounds (own entries only)
+  {
+    int ea, eb;
+    if (ta >= L::T0) { ea = ta - L::T0; eb = L::TN + (ta - L::T0); }
+    else { ea = 2 * L::TN + ta; eb = -1; }
+    qpd_init_diff<KC>(ra, lua[0], ea, K, ctl, lsx, eqm + axis * LPA);
+    qpd_init_diff<KC>(rb, lub[0], eb, K, ctl, lsx, eqm + axis * LPA);
+    const bool jvalid = ta < L::NJ;
+    const int k = jvalid ? ta / 3 : 0, rr = jvalid ? ta - 3 * k : 0;
+    const int r_old = 18 + rr;
+    const bool live = jvalid && k < K;
+    const int ooff = r_old * STR + k;
     const int eq = live ? ((eqm[axis * LPA + k] >> r_old) & 1) : 0;
-    rs[s].meta = type | (valid ? 8 : 0) | (eq ? 16 : 0) | (k << 8) | (i << 16);
-    const double *ctl = smx + L::O_CTRL;
-    rs[s].w = 0.0;
-    rs[s].l = live ? ctl[QP_SM_L * STR + rs[s].ooff] : -1.0;
-    rs[s].u = live ? ctl[QP_SM_U * STR + rs[s].ooff] : 1.0;
-    rs[s].rho = live ? ctl[QP_SM_RHO * STR + rs[s].ooff] : 0.0;
+    rj.coff = 6 * k;  // window [c_{k-1,3..5}, c_{k,0..2}] starts at QPD_CP + 6k - 3
+    rj.voff = QPD_VB * k + QPD_VC + rr;
+    rj.meta = (jvalid ? 8 : 0) | (eq ? 16 : 0) | (k << 8) | (r_old << 16);
+    rj.scale = 0.0;
+    rj.w = 0.0; rj.p = 0.0;
+    luj[0].l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
+    luj[0].u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
+    rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
   }
-  // variable thread
-  const bool isvar = ta < N;
-  const int vk = isvar ? ta / 6 : 0, vj = isvar ? ta - 6 * vk : 0;
+  const double *cej = smx + L::O_CE + 6 * (ta < L::NJ ? ta : 0);
+  // G thread (v, h); the h = 0 thread is the variable thread of v
+  const int v = ta >> 1, h = ta & 1;
+  const bool isg = v < N;
+  const bool isvar = isg && h == 0;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
   const double *vb = smx + L::O_V + QPD_VB * vk;
   const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
-  double xv = 0.0, sigv = 0.0, qv = 0.0, cDv = 0.0, tkv = 0.0, vc0 = 0.0, vc1 = 0.0, vc2 = 0.0;
-  if (isvar) {
-    const double *d = smx + L::O_LS + QPD_LS * vk;
-    qv = d[3 + vj]; sigv = d[9 + vj]; cDv = d[15 + vj];
-    tkv = smx[L::O_TK + vk];
-    const double *vcf = smx + L::O_VCF + 3 * ta;
-    vc0 = vcf[0]; vc1 = vcf[1]; vc2 = vcf[2];
-    if (vk >= K) { qv = 0.0; sigv = 0.0; cDv = 0.0; }
+  double xv = 0.0, sigv = 0.0, qv = 0.0, tkv = 0.0;
+  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);  // continuity gather coefficients (zero for unused segments)
+  if (isvar && vk < K) {
+    const double *d = lsx + QPD_LS * vk;
+    tkv = d[0]; qv = d[3 + vj]; sigv = d[9 + vj];
   }
-  double G[N];
-  if (isvar) qpd_inverse_row<KC>(smx + L::O_FS, ta, G);
-  else {
-#pragma unroll
-    for (int e = 0; e < N; e++) G[e] = 0.0;
-  }
-  sync_cta();
+  bool need_g = true;  // G is (re)built at the top of a block: after setup and after every adaptive-rho refactorisation
 
   // ---------------- ADMM ----------------
   const double alpha = o.alpha;
   int iters = 0;
   double *gv = smx + L::O_GV;
+  const double *gvh = gv + CH * h;
   double *cx = smx + L::O_C;
   double *xr = smx + L::O_XR;
   double *vv = smx + L::O_V;
-  const double *cetab = smx + L::O_CE;
-  const double *tktab = smx + L::O_TK;
-  for (int it = 1; it <= o.max_iter && state == QP_RUNNING; it++) {
-    const bool first_it = it == 1;
+  // One ADMM iteration in the fast layout (3 CTA barriers):
+  //   S2  g = A' v + sigma x - q              (V holds v = rho (2 clip(w) - w); zeros on the cold start)
+  //   S3  x~ = G g (half row per thread, the partner lane holds the other half), x = alpha x~ + (1 - alpha) x
+  //   S1  z~ = A x~ (stencils), w += alpha (z~ - clip(w)), next v -> V
+#define QPD_ITERATION()                                                                                                     \
+  do {                                                                                                                      \
+    if (isvar) gv[v] = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]) + sigv * xv - qv;                               \
+    sync_cta();                                                                                                             \
+    {                                                                                                                       \
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;                                                                        \
+      _Pragma("unroll") for (int e = 0; e + 3 < CH; e += 4) {                                                               \
+        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];         \
+      }                                                                                                                     \
+      _Pragma("unroll") for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];                                             \
+      double xt = (a0 + a1) + (a2 + a3);                                                                                    \
+      xt += sp_shfl_xor(xt, 1);                                                                                             \
+      if (isvar) {                                                                                                          \
+        xv = alpha * xt + (1.0 - alpha) * xv;                                                                               \
+        cx[QPD_CP + v] = xt;                                                                                                \
+      }                                                                                                                     \
+    }                                                                                                                       \
+    sync_cta();                                                                                                             \
+    if (ra.meta & 8) *vpa = qpd_row_update(ra, lua[0], qpd_diff_row(cpa, ra.meta & 3, ra.scale), alpha);                    \
+    if (rb.meta & 8) *vpb = qpd_row_update(rb, lub[0], qpd_diff_row(cpb, rb.meta & 3, rb.scale), alpha);                    \
+    if (rj.meta & 8) *vpj = qpd_row_update(rj, luj[0], qpd_join_row(cpj, cej), alpha);                                      \
+    sync_cta();                                                                                                             \
+  } while (0)
+
+  // The loop is blocked by check interval: the inner loop contains no calls, so that the half row of G and the
+  // row state stay in registers; G's master copy lives in local memory (Gl) and is reloaded once per block.
+  const double *cpa = cx + ra.coff, *cpb = cx + rb.coff, *cpj = cx + rj.coff;  // stencil windows of the row slots
+  double *vpa = vv + ra.voff, *vpb = vv + rb.voff, *vpj = vv + rj.voff;        // their V entries
+  double Gl[CH];
+  int it = 1;
+  while (it <= o.max_iter && state == QP_RUNNING) {
+    if (need_g) {
+      qpd_build_g<KC>(smx + L::O_FS, isg ? v : 0, h, isg, Gl);
+      need_g = false;
+    }
+    double G[CH];
+#pragma unroll
+    for (int e = 0; e < CH; e++) G[e] = Gl[e];
+    int it_end = o.max_iter;  // last iteration of this block (inclusive): the next check iteration
+    if (o.check_every > 0) {
+      const int nxt = ((it + o.check_every - 1) / o.check_every) * o.check_every;
+      it_end = nxt < it_end ? nxt : it_end;
+    }
+    for (; it < it_end; it++) QPD_ITERATION();
     const bool check = (o.check_every > 0) && (it % o.check_every == 0);
-    // S2: right-hand side g = A' v + sigma x - q  (V holds v = rho (2 clip(w) - w); zeros on the cold start)
-    if (isvar) gv[ta] = qpd_gather(vb, vkk, vj, tkv, vc0, vc1, vc2) + sigv * xv - qv;
-    sync_cta();
-    // S3: x~ = G g, relaxation
-    if (isvar) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int e = 0; e < N; e += 4) {
-        a0 += G[e] * gv[e]; a1 += G[e + 1] * gv[e + 1]; a2 += G[e + 2] * gv[e + 2]; a3 += G[e + 3] * gv[e + 3];
-      }
-      const double xt = (a0 + a1) + (a2 + a3);
-      xv = alpha * xt + (1.0 - alpha) * xv;
-      cx[3 + ta] = xt;
-    }
-    sync_cta();
-    // S1: z~ = A x~, w update, next v (check iterations: delta y instead of v)
-    double red_v[QPD_NRED];
-#pragma unroll
-    for (int i = 0; i < QPD_NRED; i++) red_v[i] = 0.0;
-    const double c_over_rhobar = c_scale / rhobar;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      const int meta = rs[s].meta;
-      if (!(meta & 8)) continue;
-      const int type = meta & 7, k = (meta >> 8) & 0xff, i = meta >> 16;
-      const double zt = qpd_row(type, cx + rs[s].coff, tktab[k], cetab + 18 * k + 6 * i);
-      const double w = rs[s].w, l = rs[s].l, u = rs[s].u, rho = rs[s].rho;
-      const double p = first_it ? 0.0 : qpd_clip(w, l, u);
-      const double wn = first_it ? alpha * zt : w + alpha * (zt - p);
-      const double pn = qpd_clip(wn, l, u);
-      rs[s].w = wn;
-      if (!check) {
-        vv[rs[s].voff] = rho * (2.0 * pn - wn);
-      } else {
-        const double yo = first_it ? 0.0 : rho * (w - p);
-        const double dy = rho * (wn - pn) - yo;
-        vv[rs[s].voff] = dy;
-        if (rho > 0.0) {
-          const double Er = sqrt(rho * c_over_rhobar * ((meta & 16) ? 1e-3 : 1.0));
-          red_v[7] = fmax(red_v[7], fabs(c_scale * dy / Er));
-          red_v[9] += c_scale * (u * fmax(dy, 0.0) + l * fmin(dy, 0.0));
-        }
-      }
-    }
+    // check iterations keep the old multipliers y = rho (w - clip(w)) for delta y
+    double yo_a = 0.0, yo_b = 0.0, yo_j = 0.0;
+    if (check) { yo_a = ra.rho * (ra.w - ra.p); yo_b = rb.rho * (rb.w - rb.p); yo_j = rj.rho * (rj.w - rj.p); }
+    QPD_ITERATION();
     iters = it;
-    sync_cta();
+    it++;
     if (!check) continue;
 
-    // ---------------- termination / infeasibility check (OSQP, scaled space, joint over both axes) ----------------
-    if (isvar) {
-      const double atd = qpd_gather(vb, vkk, vj, tkv, vc0, vc1, vc2);
-      red_v[8] = fabs(cDv * atd);
-      xr[3 + ta] = xv;
-    }
-    sync_cta();
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      if (!(rs[s].meta & 8)) continue;
-      const double w = rs[s].w;
-      vv[rs[s].voff] = rs[s].rho * (w - qpd_clip(w, rs[s].l, rs[s].u));  // y
-    }
-    sync_cta();
-    if (isvar) {
-      const double aty = qpd_gather(vb, vkk, vj, tkv, vc0, vc1, vc2);
-      double px = 0.0;
-      const double *pk = smx + L::O_CTRL + QP_SM_P * STR + vk;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const int e = (i >= vj) ? LT(i, vj) : LT(vj, i);
-        px += pk[e * STR] * xr[3 + 6 * vk + i];
-      }
-      if (vk >= K) px = 0.0;
-      red_v[1] = cDv * fabs(px + qv + aty);
-      red_v[4] = cDv * fabs(qv);
-      red_v[5] = cDv * fabs(px);
-      red_v[6] = cDv * fabs(aty);
-    }
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      const int meta = rs[s].meta;
-      if (!(meta & 8) || !(rs[s].rho > 0.0)) continue;
-      const int type = meta & 7, k = (meta >> 8) & 0xff, i = meta >> 16;
-      const double ax = qpd_row(type, xr + rs[s].coff, tktab[k], cetab + 18 * k + 6 * i);
-      const double z = qpd_clip(rs[s].w, rs[s].l, rs[s].u);
-      const double Er = sqrt(rs[s].rho * c_over_rhobar * ((meta & 16) ? 1e-3 : 1.0));
-      red_v[0] = fmax(red_v[0], Er * fabs(ax - z));
-      red_v[2] = fmax(red_v[2], Er * fabs(z));
-      red_v[3] = fmax(red_v[3], Er * fabs(ax));
-    }
-    qpd_reduce(red_v, red, warp, lane, L::NWARPS, sync_cta);
-    const double pri = red_v[0], dua = red_v[1], nz = red_v[2], nax = red_v[3], nq = red_v[4], npx = red_v[5], naty = red_v[6];
-    const double nd = red_v[7], na = red_v[8], lhs = red_v[9];
-    const double eps_p = o.eps_abs + o.eps_rel * fmax(nz, nax);
-    const double eps_d = o.eps_abs + o.eps_rel * fmax(nq, fmax(npx, naty));
-    if (pri < eps_p && dua < eps_d) state = QP_ST_SOLVED;
-    else if (!(pri < eps_p) && nd > o.eps_pinf && lhs < -o.eps_pinf * nd && na < o.eps_pinf * nd) state = QP_ST_INFEASIBLE;
-    // adaptive rho (OSQP's rule, every adaptive_rho_interval iterations)
-    if (state == QP_RUNNING && o.adapt_every > 0 && (it % o.adapt_every == 0)) {
-      const double pr = pri / (fmax(nz, nax) + 1e-10);
-      const double dr = dua / (fmax(nq, fmax(npx, naty)) + 1e-10);
-      double est = rhobar * sqrt(pr / (dr + 1e-10));
-      est = fmin(fmax(est, 1e-6), 1e6);
-      if (est > rhobar * o.adapt_tol || est < rhobar / o.adapt_tol) {
-        const double ratio = est / rhobar;
-        double *ctl = smx + L::O_CTRL;
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-          if (!(rs[s].meta & 8)) continue;
-          const double w = rs[s].w, z = qpd_clip(w, rs[s].l, rs[s].u);
-          rs[s].w = z + (w - z) / ratio;  // keep (z, y): w' = z + y / rho'
-          rs[s].rho *= ratio;
-          if (((rs[s].meta >> 8) & 0xff) < K) ctl[QP_SM_RHO * STR + rs[s].ooff] = rs[s].rho;
-        }
-        rhobar = est;
-        sync_cta();
-        if (warp == 0) qpd_control_refactor<KC>(a, slot, lane, smem, c_scale, rhobar);
-        sync_cta();
-        if (red[0] != 0.0) state = QP_ST_INFEASIBLE;
-        if (isvar) qpd_inverse_row<KC>(smx + L::O_FS, ta, G);
-        sync_cta();
-      }
+    // ---------------- termination / infeasibility check + adaptive rho (out of line, see qpd_check) ----------------
+    {
+      QpdCheckIO io;
+      io.rows[0] = ra; io.rows[1] = rb; io.rows[2] = rj;
+      io.yo[0] = yo_a; io.yo[1] = yo_b; io.yo[2] = yo_j;
+      io.xv = xv; io.qv = qv; io.tkv = tkv; io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 0; io.it = iters;
+      qpd_check<KC>(a, slot, tid, smem, io, sync_cta);
+      ra = io.rows[0]; rb = io.rows[1]; rj = io.rows[2];
+      rhobar = io.rhobar; state = io.state;
+      if (io.need_g) need_g = true;
     }
     // V must hold v = rho (2 clip(w) - w) again for the next iteration
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      if (!(rs[s].meta & 8)) continue;
-      const double w = rs[s].w;
-      vv[rs[s].voff] = rs[s].rho * (2.0 * qpd_clip(w, rs[s].l, rs[s].u) - w);
-    }
+    if (ra.meta & 8) vv[ra.voff] = ra.rho * (2.0 * ra.p - ra.w);
+    if (rb.meta & 8) vv[rb.voff] = rb.rho * (2.0 * rb.p - rb.w);
+    if (rj.meta & 8) vv[rj.voff] = rj.rho * (2.0 * rj.p - rj.w);
     sync_cta();
   }
 
-  // ---------------- hand the iterate back to the lane-per-segment layout: W slots, x ----------------
+#undef QPD_ITERATION
+  // ---------------- hand the iterate back to the lane-per-segment layout: W slots, rho, x ----------------
   {
-    double *ctl = smx + L::O_CTRL;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      if (!(rs[s].meta & 8) || ((rs[s].meta >> 8) & 0xff) >= K) continue;
-      ctl[QP_SM_W * STR + rs[s].ooff] = rs[s].w;
-      ctl[QP_SM_RHO * STR + rs[s].ooff] = rs[s].rho;
-    }
-    if (isvar) xr[3 + ta] = xv;
+    double *ctlw = smx + L::O_CTRL;
+    qpd_handback_row(ra, K, ctlw, STR);
+    qpd_handback_row(rb, K, ctlw, STR);
+    qpd_handback_row(rj, K, ctlw, STR);
+    if (isvar) xr[QPD_CP + v] = xv;
   }
   sync_cta();
   if (warp != 0) return;

@@ -88,7 +88,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
     if (cls <= 3 && !force_lanes) {
       // dense kernel: one CTA of 2 TA threads per scenario
       const int total = cls == 0 ? QpdLayout<8>::TOTAL : cls == 1 ? QpdLayout<10>::TOTAL : cls == 2 ? QpdLayout<12>::TOTAL : QpdLayout<16>::TOTAL;
-      const int nwarps = cls <= 1 ? 4 : 6;
+      const int nwarps = cls == 0 ? QpdLayout<8>::NWARPS : cls == 1 ? QpdLayout<10>::NWARPS : cls == 2 ? QpdLayout<12>::NWARPS : QpdLayout<16>::NWARPS;
       for (int slot = 0; slot < cnt; slot++) {
         std::vector<double> sm(total + 2);
         double *base = sm.data();

@@ -24,11 +24,21 @@ def stats(variant, batch, w, planner):
     both = got.verified() & ok1 & (ref["polish"] == 2)
     d = np.abs(got.ctrl[both] - ref["ctrl"][both])
     rel = d / (1e-6 + 1e-5 * np.abs(ref["ctrl"][both]))
+    worst = []
+    if rel.size:
+        per = rel.max(axis=1)
+        idx = np.nonzero(both)[0]
+        for j in np.argsort(-per)[:5]:
+            b = int(idx[j])
+            worst.append(dict(b=b, ratio=float(per[j]), absdiff=float(d[j].max()), K=int(got.K[b]), gpu_iters=int(got.iters[b]),
+                              ref0_iters=int(ref0["iters"][b]), ref1_iters=int(ref["iters"][b]), gpu_status=int(got.status[b]),
+                              obj_gpu=float(got.obj[b]), obj_ref=float(ref["obj"][b])))
     it_same = (got.iters == ref0["iters"])
     return dict(B=int(batch.batch), gpu_ok=int(got.ok().sum()), ref0_ok=int(ok0.sum()), ref1_ok=int(ok1.sum()),
                 decided=int(dec.sum()), mismatch_decided=int((mism & dec).sum()), mismatch_undecided=int((mism & ~dec).sum()),
                 gpu_verified=int(got.verified().sum()), ref_verified=int((ok1 & (ref["polish"] == 2)).sum()),
-                verified_both=int(both.sum()), max_tol_ratio=float(rel.max()) if rel.size else 0.0,
+                verified_both=int(both.sum()), max_tol_ratio=float(rel.max()) if rel.size else 0.0, worst=worst,
+                solved0=int((got.status == 0).sum()), solved0_verified=int(((got.status == 0) & got.verified()).sum()),
                 iters_equal=int(it_same.sum()), iters_close=int((np.abs(got.iters - ref0["iters"]) <= 100).sum()),
                 gpu_mean_iters=float(got.iters.mean()), ref0_mean_iters=float(ref0["iters"].mean()),
                 gpu_status_hist=np.bincount(got.status, minlength=6).tolist(),

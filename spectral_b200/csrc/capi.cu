@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
 
 // dense-operator ADMM kernel (qp_dense.cuh): one CTA (2 TA threads) per scenario of this class
 #ifndef QPD_MINBLOCKS
-#define QPD_MINBLOCKS(KC) ((KC) <= 10 ? 2 : 1)
+#define QPD_MINBLOCKS(KC) ((KC) <= 10 ? 2 : 1)  // CTAs per SM the register budget is capped for
 #endif
 template <int KC>
 __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, QPD_MINBLOCKS(KC)) k_qpd(const QpArgs a) {

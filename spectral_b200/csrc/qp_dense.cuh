@@ -44,20 +44,34 @@
 #define QPD_LS 24         // doubles of lane state per segment: t, tp, tn, q[6], sig[6], cD[6]
 #define QPD_NRED 10
 
+// Chunks per row of G (= threads per variable).  Measured on B200 (profiles/r1_qpd_nch.md): 2 chunks beat 4 for the
+// common K <= 8 class -- with 4, the warps run the variable gather with a quarter of their lanes and the total
+// instruction / shared-memory wavefront count per iteration rises 59 % / 69 %.  4 chunks (a quarter row of G and at
+// most one constraint row per thread) are kept where 2 would not fit the register file (KC >= 12).
+#ifndef QPD_NCH
+#define QPD_NCH(KC) ((KC) >= 12 ? 4 : 2)
+#endif
+SP_HD constexpr int qpd_nch(int KC) { return QPD_NCH(KC); }
+
 template <int KC>
 struct QpdLayout {
-  static_assert(KC % 2 == 0, "the two half rows of G split the segments evenly");
+  static constexpr int NCH = qpd_nch(KC);      // threads per variable (chunks per row of G)
+  static_assert(KC % NCH == 0, "the chunks of a row of G split the segments evenly");
   static constexpr int N = 6 * KC;             // variables per axis
-  static constexpr int CH = N / 2;             // columns of G per thread
-  static constexpr int KB = KC / 2;            // segments per half row
+  static constexpr int CH = N / NCH;           // columns of G per thread
+  static constexpr int KB = KC / NCH;          // segments per chunk
   static constexpr int ROWS = 21 * KC;         // constraint rows per axis
   static constexpr int NN = 18 * KC;           // difference rows (containment, velocity, acceleration, jerk)
   static constexpr int NJ = 3 * KC;            // continuity / initial-state rows
-  static constexpr int TA = ((2 * N + 31) / 32) * 32;  // threads per axis problem
-  static constexpr int NWARPS = 2 * TA / 32;           // warps per CTA
-  static constexpr int T0 = ((NJ + 31) / 32) * 32;     // first thread without a continuity row
-  static constexpr int TN = TA - T0;                   // threads that own two difference rows
-  static_assert(2 * TN + T0 >= NN, "row slots");
+  static constexpr int TA = ((NCH * N + 31) / 32) * 32;  // threads per axis problem
+  static constexpr int NWARPS = 2 * TA / 32;             // warps per CTA
+  // row slots.  NCH = 2: threads [T0, TA) own two difference rows (slots A, B), threads [0, T0) one difference row
+  // (slot A) and, below NJ, one continuity row (slot J).  NCH = 4: thread t owns difference row t (t < NN) or
+  // continuity row t - NN.
+  static constexpr bool TWO_SLOTS = NCH == 2;
+  static constexpr int T0 = TWO_SLOTS ? ((NJ + 31) / 32) * 32 : 0;
+  static constexpr int TN = TA - T0;
+  static_assert(TWO_SLOTS ? (2 * TN + T0 >= NN) : (TA >= ROWS), "row slots");
   static constexpr int LPA = KC <= 8 ? 8 : 16; // lanes per axis of the lane-per-segment (control) code
   static constexpr int STR = LPA;              // its shared-memory stride
   // per-axis shared memory (doubles)
@@ -125,17 +139,17 @@ struct QpdRow {
   int meta;                // bits 0-1 difference order, bit 3 valid, bit 4 equality row, bits 8-15 segment, 16.. row in slots (r)
 };
 
-// Half row h of G = S^-1 for variable v: the thread pair (v, 0), (v, 1) runs the block forward / backward
-// substitution of qp.cuh's factor (read from shared memory, broadcast) on e_v, each on its own half of
-// the segments, handing the 3-value carry to the partner lane by shuffle.
+// Chunk h of row v of G = S^-1: the NCH threads (v, 0..NCH-1), adjacent lanes, run the block forward / backward
+// substitution of qp.cuh's factor (read from shared memory, broadcast) on e_v, each on its own KC/NCH segments,
+// handing the 3-value carry to the neighbour lane by shuffle.
 template <int KC>
-SP_DEV void qpd_inverse_half_row(const double *fs, int v, int h, double *g) {
-  constexpr int KB = KC / 2;
+SP_DEV void qpd_inverse_chunk(const double *fs, int v, int h, double *g) {
+  constexpr int KB = QpdLayout<KC>::KB, NCH = QpdLayout<KC>::NCH;
   const int kv = v / 6, iv = v - 6 * kv;
   const int kbase = h * KB;
   double c3 = 0.0, c4 = 0.0, c5 = 0.0;  // y_{k-1}[3..5]
 #pragma unroll
-  for (int phase = 0; phase < 2; phase++) {
+  for (int phase = 0; phase < NCH; phase++) {
     if (h == phase) {
 #pragma unroll
       for (int kb = 0; kb < KB; kb++) {
@@ -151,11 +165,14 @@ SP_DEV void qpd_inverse_half_row(const double *fs, int v, int h, double *g) {
         c3 = g[6 * kb + 3]; c4 = g[6 * kb + 4]; c5 = g[6 * kb + 5];
       }
     }
-    if (phase == 0) { c3 = sp_shfl_xor(c3, 1); c4 = sp_shfl_xor(c4, 1); c5 = sp_shfl_xor(c5, 1); }
+    if (phase + 1 < NCH) {  // lane h + 1 takes over with lane h's carry
+      const double t3 = sp_shfl_up(c3, 1, NCH), t4 = sp_shfl_up(c4, 1, NCH), t5 = sp_shfl_up(c5, 1, NCH);
+      if (h == phase + 1) { c3 = t3; c4 = t4; c5 = t5; }
+    }
   }
   double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // x_{k+1}[0..2]
 #pragma unroll
-  for (int phase = 1; phase >= 0; phase--) {
+  for (int phase = NCH - 1; phase >= 0; phase--) {
     if (h == phase) {
 #pragma unroll
       for (int kb = KB - 1; kb >= 0; kb--) {
@@ -172,7 +189,10 @@ SP_DEV void qpd_inverse_half_row(const double *fs, int v, int h, double *g) {
         n0 = g[6 * kb + 0]; n1 = g[6 * kb + 1]; n2 = g[6 * kb + 2];
       }
     }
-    if (phase == 1) { n0 = sp_shfl_xor(n0, 1); n1 = sp_shfl_xor(n1, 1); n2 = sp_shfl_xor(n2, 1); }
+    if (phase > 0) {  // lane h - 1 takes over with lane h's x
+      const double t0 = sp_shfl_down(n0, 1, NCH), t1 = sp_shfl_down(n1, 1, NCH), t2 = sp_shfl_down(n2, 1, NCH);
+      if (h == phase - 1) { n0 = t0; n1 = t1; n2 = t2; }
+    }
   }
 }
 
@@ -335,7 +355,7 @@ SP_DEV void qpd_decode_diff(int e, int &order, int &k, int &i) {
 template <int KC>
 SP_DEV_NOINLINE void qpd_build_g(const double *fs, int v, int h, bool isg, double *out) {
   double g[QpdLayout<KC>::CH];
-  qpd_inverse_half_row<KC>(fs, v, h, g);
+  qpd_inverse_chunk<KC>(fs, v, h, g);
 #pragma unroll
   for (int e = 0; e < QpdLayout<KC>::CH; e++) out[e] = isg ? g[e] : 0.0;
 }
@@ -406,20 +426,86 @@ SP_DEV double qpd_row_update(QpdRow &r, const QpdLU &b, double zt, double alpha)
   return r.rho * (2.0 * pn - wn);
 }
 
-// Everything a check iteration needs from the hot loop, passed through local memory (the call is out of
-// line so that its register needs do not weigh on the loop).
-struct QpdCheckIO {
-  QpdRow rows[3];   // in: the thread's row slots; out: w and rho (adaptive rho rescales them)
-  double yo[3];     // multipliers before this iteration's update
-  double xv, qv, tkv, c_scale, rhobar;
+// The per-thread state of the dense loop.  It lives in local memory in the CTA body; qpd_block loads what it needs
+// into registers for a block of iterations, qpd_check / qpd_build_g work on it in place.
+template <int CHN>
+struct QpdIOT {
+  double G[CHN];    // this thread's chunk of its row of G = S^-1
+  QpdRow rows[3];   // row slots: two difference rows (A, B) and one continuity row (J); unused ones have meta bit 3 clear
+  double yo[3];     // multipliers before the check iteration's update
+  double xv, sigv, qv, tkv;  // variable thread: relaxed iterate, sigma, q, segment duration
+  double c_scale, rhobar;
   int state, need_g, it;
 };
+
+// A block of `n` ADMM iterations in the fast layout (3 CTA barriers each), out of line: only the hot state is live.
+//   S2  g = A' v + sigma x - q              (V holds v = rho (2 clip(w) - w); zeros on the cold start)
+//   S3  x~ = G g (one chunk of the row per thread, the partner lanes hold the others), x = alpha x~ + (1 - alpha) x
+//   S1  z~ = A x~ (stencils), w += alpha (z~ - clip(w)), next v -> V
+template <int KC, typename SyncFn>
+SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+  using L = QpdLayout<KC>;
+  constexpr int N = L::N, CH = L::CH, TA = L::TA;
+  const int v = ta / L::NCH, h = ta % L::NCH;
+  const bool isg = v < N;
+  const bool isvar = isg && h == 0;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
+  const double *vb = smx + L::O_V + QPD_VB * vk;
+  const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
+  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);  // continuity gather coefficients (zero for unused segments)
+  double *gvp = smx + L::O_GV + (isg ? v : 0);
+  const double *gvh = smx + L::O_GV + CH * h;
+  double *cx = smx + L::O_C;
+  double *cxp = cx + QPD_CP + (isg ? v : 0);
+  double *vv = smx + L::O_V;
+  const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
+  QpdRow ra = io.rows[0], rb = io.rows[1], rj = io.rows[2];
+  const double *cej = smx + L::O_CE + 6 * ((rj.meta & 8) ? 3 * ((rj.meta >> 8) & 0xff) + ((rj.meta >> 16) - 18) : 0);
+  const double *cpa = cx + ra.coff, *cpb = cx + rb.coff, *cpj = cx + rj.coff;  // stencil windows of the row slots
+  double *vpa = vv + ra.voff, *vpb = vv + rb.voff, *vpj = vv + rj.voff;        // their V entries
+  const bool va = ra.meta & 8, vbb = L::TWO_SLOTS && (rb.meta & 8), vjj = rj.meta & 8;
+  const int oa = ra.meta & 3, ob = rb.meta & 3;
+  double xv = io.xv;
+  const double sigv = io.sigv, qv = io.qv, tkv = io.tkv;
+  double G[CH];
+#pragma unroll
+  for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  for (int i = 0; i < n; i++) {
+    if (isvar) *gvp = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]) + sigv * xv - qv;
+    sync_cta();
+    {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int e = 0; e + 3 < CH; e += 4) {
+        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];
+      }
+#pragma unroll
+      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];
+      double xt = (a0 + a1) + (a2 + a3);
+      xt += sp_shfl_xor(xt, 1);
+      if (L::NCH == 4) xt += sp_shfl_xor(xt, 2);
+      if (isvar) {
+        xv = alpha * xt + (1.0 - alpha) * xv;
+        *cxp = xt;
+      }
+    }
+    sync_cta();
+    if (va) *vpa = qpd_row_update(ra, lua[0], qpd_diff_row(cpa, oa, ra.scale), alpha);
+    if (vbb) *vpb = qpd_row_update(rb, lub[0], qpd_diff_row(cpb, ob, rb.scale), alpha);
+    if (vjj) *vpj = qpd_row_update(rj, luj[0], qpd_join_row(cpj, cej), alpha);
+    sync_cta();
+  }
+  io.rows[0].w = ra.w; io.rows[0].p = ra.p;
+  io.rows[1].w = rb.w; io.rows[1].p = rb.p;
+  io.rows[2].w = rj.w; io.rows[2].p = rj.p;
+  io.xv = xv;
+}
 
 // OSQP's termination test (residuals in the scaled space, scaled_termination = 1), primal-infeasibility
 // certificate and adaptive-rho rule, evaluated CTA-wide = jointly over the s and l problems of the scenario.
 // Called by all threads of the CTA on check iterations.
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem, QpdCheckIO &io, SyncFn sync_cta) {
+SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem, QpdIOT<QpdLayout<KC>::CH> &io, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int N = L::N, LPA = L::LPA, STR = L::STR, TA = L::TA;
   (void)LPA;
@@ -432,8 +518,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   const double *ctl = smx + L::O_CTRL;
   const double *lsx = smx + L::O_LS;
   const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
-  const double *cej = smx + L::O_CE + 6 * (ta < L::NJ ? ta : 0);
-  const int v = ta >> 1, h = ta & 1;
+  const double *cej = smx + L::O_CE + 6 * ((io.rows[2].meta & 8) ? 3 * ((io.rows[2].meta >> 8) & 0xff) + ((io.rows[2].meta >> 16) - 18) : 0);
+  const int v = ta / L::NCH, h = ta % L::NCH;
   const bool isg = v < N;
   const bool isvar = isg && h == 0;
   const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
@@ -547,19 +633,26 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
   state = (int)red[1];
   sync_cta();
 
-  // ---------------- fast-layout state ----------------
+  // ---------------- fast-layout state (lives in local memory; qpd_block keeps it in registers while it iterates) ----------------
   const double *ctl = smx + L::O_CTRL;
   const double *lsx = smx + L::O_LS;
-  QpdRow ra, rb, rj;  // two difference-row slots and the continuity-row slot of this thread
-  QpdLU *lua = (QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;  // their bounds (own entries only)
+  QpdIOT<CH> io;
+  QpdLU *lua = (QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;  // bounds of this thread's row slots
   {
-    int ea, eb;
-    if (ta >= L::T0) { ea = ta - L::T0; eb = L::TN + (ta - L::T0); }
-    else { ea = 2 * L::TN + ta; eb = -1; }
-    qpd_init_diff<KC>(ra, lua[0], ea, K, ctl, lsx, eqm + axis * LPA);
-    qpd_init_diff<KC>(rb, lub[0], eb, K, ctl, lsx, eqm + axis * LPA);
-    const bool jvalid = ta < L::NJ;
-    const int k = jvalid ? ta / 3 : 0, rr = jvalid ? ta - 3 * k : 0;
+    int ea, eb, ej;
+    if (L::TWO_SLOTS) {
+      if (ta >= L::T0) { ea = ta - L::T0; eb = L::TN + (ta - L::T0); }
+      else { ea = 2 * L::TN + ta; eb = -1; }
+      ej = ta < L::NJ ? ta : -1;
+    } else {
+      ea = ta < L::NN ? ta : -1; eb = -1;
+      ej = (ta >= L::NN && ta < L::ROWS) ? ta - L::NN : -1;
+    }
+    qpd_init_diff<KC>(io.rows[0], lua[0], ea, K, ctl, lsx, eqm + axis * LPA);
+    qpd_init_diff<KC>(io.rows[1], lub[0], eb, K, ctl, lsx, eqm + axis * LPA);
+    QpdRow &rj = io.rows[2];
+    const bool jvalid = ej >= 0;
+    const int k = jvalid ? ej / 3 : 0, rr = jvalid ? ej - 3 * k : 0;
     const int r_old = 18 + rr;
     const bool live = jvalid && k < K;
     const int ooff = r_old * STR + k;
@@ -573,106 +666,60 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     luj[0].u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
     rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
   }
-  const double *cej = smx + L::O_CE + 6 * (ta < L::NJ ? ta : 0);
   // G thread (v, h); the h = 0 thread is the variable thread of v
-  const int v = ta >> 1, h = ta & 1;
+  const int v = ta / L::NCH, h = ta % L::NCH;
   const bool isg = v < N;
   const bool isvar = isg && h == 0;
   const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
-  const double *vb = smx + L::O_V + QPD_VB * vk;
-  const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
-  double xv = 0.0, sigv = 0.0, qv = 0.0, tkv = 0.0;
-  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);  // continuity gather coefficients (zero for unused segments)
+  io.xv = 0.0; io.sigv = 0.0; io.qv = 0.0; io.tkv = 0.0;
   if (isvar && vk < K) {
     const double *d = lsx + QPD_LS * vk;
-    tkv = d[0]; qv = d[3 + vj]; sigv = d[9 + vj];
+    io.tkv = d[0]; io.qv = d[3 + vj]; io.sigv = d[9 + vj];
   }
-  bool need_g = true;  // G is (re)built at the top of a block: after setup and after every adaptive-rho refactorisation
+  io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 1; io.it = 0;
+  sync_cta();
 
   // ---------------- ADMM ----------------
-  const double alpha = o.alpha;
+  // Blocked by check interval: qpd_block runs the plain iterations out of line with only the hot state live (the chunk
+  // of G, the row slots, the variable) -- no spills in the loop; the check iteration is one more single-iteration
+  // block bracketed by the multiplier capture and qpd_check.
   int iters = 0;
-  double *gv = smx + L::O_GV;
-  const double *gvh = gv + CH * h;
-  double *cx = smx + L::O_C;
-  double *xr = smx + L::O_XR;
-  double *vv = smx + L::O_V;
-  // One ADMM iteration in the fast layout (3 CTA barriers):
-  //   S2  g = A' v + sigma x - q              (V holds v = rho (2 clip(w) - w); zeros on the cold start)
-  //   S3  x~ = G g (half row per thread, the partner lane holds the other half), x = alpha x~ + (1 - alpha) x
-  //   S1  z~ = A x~ (stencils), w += alpha (z~ - clip(w)), next v -> V
-#define QPD_ITERATION()                                                                                                     \
-  do {                                                                                                                      \
-    if (isvar) gv[v] = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]) + sigv * xv - qv;                               \
-    sync_cta();                                                                                                             \
-    {                                                                                                                       \
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;                                                                        \
-      _Pragma("unroll") for (int e = 0; e + 3 < CH; e += 4) {                                                               \
-        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];         \
-      }                                                                                                                     \
-      _Pragma("unroll") for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];                                             \
-      double xt = (a0 + a1) + (a2 + a3);                                                                                    \
-      xt += sp_shfl_xor(xt, 1);                                                                                             \
-      if (isvar) {                                                                                                          \
-        xv = alpha * xt + (1.0 - alpha) * xv;                                                                               \
-        cx[QPD_CP + v] = xt;                                                                                                \
-      }                                                                                                                     \
-    }                                                                                                                       \
-    sync_cta();                                                                                                             \
-    if (ra.meta & 8) *vpa = qpd_row_update(ra, lua[0], qpd_diff_row(cpa, ra.meta & 3, ra.scale), alpha);                    \
-    if (rb.meta & 8) *vpb = qpd_row_update(rb, lub[0], qpd_diff_row(cpb, rb.meta & 3, rb.scale), alpha);                    \
-    if (rj.meta & 8) *vpj = qpd_row_update(rj, luj[0], qpd_join_row(cpj, cej), alpha);                                      \
-    sync_cta();                                                                                                             \
-  } while (0)
-
-  // The loop is blocked by check interval: the inner loop contains no calls, so that the half row of G and the
-  // row state stay in registers; G's master copy lives in local memory (Gl) and is reloaded once per block.
-  const double *cpa = cx + ra.coff, *cpb = cx + rb.coff, *cpj = cx + rj.coff;  // stencil windows of the row slots
-  double *vpa = vv + ra.voff, *vpb = vv + rb.voff, *vpj = vv + rj.voff;        // their V entries
-  double Gl[CH];
   int it = 1;
-  while (it <= o.max_iter && state == QP_RUNNING) {
-    if (need_g) {
-      qpd_build_g<KC>(smx + L::O_FS, isg ? v : 0, h, isg, Gl);
-      need_g = false;
+  double *vv = smx + L::O_V;
+  while (it <= o.max_iter && io.state == QP_RUNNING) {
+    if (io.need_g) {  // after setup and after every adaptive-rho refactorisation
+      qpd_build_g<KC>(smx + L::O_FS, isg ? v : 0, h, isg, io.G);
+      io.need_g = 0;
     }
-    double G[CH];
-#pragma unroll
-    for (int e = 0; e < CH; e++) G[e] = Gl[e];
     int it_end = o.max_iter;  // last iteration of this block (inclusive): the next check iteration
     if (o.check_every > 0) {
       const int nxt = ((it + o.check_every - 1) / o.check_every) * o.check_every;
       it_end = nxt < it_end ? nxt : it_end;
     }
-    for (; it < it_end; it++) QPD_ITERATION();
-    const bool check = (o.check_every > 0) && (it % o.check_every == 0);
+    const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
+    if (it_end > it) qpd_block<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
     // check iterations keep the old multipliers y = rho (w - clip(w)) for delta y
-    double yo_a = 0.0, yo_b = 0.0, yo_j = 0.0;
-    if (check) { yo_a = ra.rho * (ra.w - ra.p); yo_b = rb.rho * (rb.w - rb.p); yo_j = rj.rho * (rj.w - rj.p); }
-    QPD_ITERATION();
-    iters = it;
-    it++;
+#pragma unroll
+    for (int r = 0; r < 3; r++) io.yo[r] = io.rows[r].rho * (io.rows[r].w - io.rows[r].p);
+    qpd_block<KC>(io, smx, ta, 1, o.alpha, sync_cta);
+    iters = it_end;
+    it = it_end + 1;
     if (!check) continue;
-
-    // ---------------- termination / infeasibility check + adaptive rho (out of line, see qpd_check) ----------------
-    {
-      QpdCheckIO io;
-      io.rows[0] = ra; io.rows[1] = rb; io.rows[2] = rj;
-      io.yo[0] = yo_a; io.yo[1] = yo_b; io.yo[2] = yo_j;
-      io.xv = xv; io.qv = qv; io.tkv = tkv; io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 0; io.it = iters;
-      qpd_check<KC>(a, slot, tid, smem, io, sync_cta);
-      ra = io.rows[0]; rb = io.rows[1]; rj = io.rows[2];
-      rhobar = io.rhobar; state = io.state;
-      if (io.need_g) need_g = true;
-    }
+    // termination / infeasibility check + adaptive rho (out of line, see qpd_check)
+    io.it = iters;
+    qpd_check<KC>(a, slot, tid, smem, io, sync_cta);
     // V must hold v = rho (2 clip(w) - w) again for the next iteration
-    if (ra.meta & 8) vv[ra.voff] = ra.rho * (2.0 * ra.p - ra.w);
-    if (rb.meta & 8) vv[rb.voff] = rb.rho * (2.0 * rb.p - rb.w);
-    if (rj.meta & 8) vv[rj.voff] = rj.rho * (2.0 * rj.p - rj.w);
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      if (io.rows[r].meta & 8) vv[io.rows[r].voff] = io.rows[r].rho * (2.0 * io.rows[r].p - io.rows[r].w);
     sync_cta();
   }
+  state = io.state;
+  rhobar = io.rhobar;
+  const QpdRow &ra = io.rows[0], &rb = io.rows[1], &rj = io.rows[2];
+  const double xv = io.xv;
+  double *xr = smx + L::O_XR;
 
-#undef QPD_ITERATION
   // ---------------- hand the iterate back to the lane-per-segment layout: W slots, rho, x ----------------
   {
     double *ctlw = smx + L::O_CTRL;

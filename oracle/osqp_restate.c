@@ -528,7 +528,10 @@ static int polish(Work *w, double *pol_x, double *pol_y_full, int *n_active_out,
     double delta = w->s->delta;
     for (ll a = 0; a < k; a++) dneg[a] = -delta;
     Kkt K; Ldl F; memset(&F, 0, sizeof(F));
-    kkt_build(&K, &w->P, &Ar, delta, dneg, n, k);
+    /* converged-oracle mode (polish_rounds > 1): the primal regularisation is decoupled from delta and kept
+     * tiny -- with delta on both blocks the refinement is a proximal iteration that stalls along the weakly
+     * curved directions of P (scaled eigenvalues ~1e-9 on these problems) */
+    kkt_build(&K, &w->P, &Ar, rounds > 1 ? 1e-12 : delta, dneg, n, k);
     ldl_symbolic(&F, K.dim, K.p, K.i);
     ok = ldl_numeric(&F, K.p, K.i, K.x) == 0;
     if (ok) {
@@ -563,7 +566,24 @@ static int polish(Work *w, double *pol_x, double *pol_y_full, int *n_active_out,
         if ((act[i] < 0 && yi > tol_d) || (act[i] > 0 && yi < -tol_d)) { act[i] = 0; changed++; }
       }
     }
-    if (!changed) { *verified = 1; break; }
+    /* stationarity and active-row feasibility of the point must hold too before "no change" counts as a
+     * KKT proof: on ill-conditioned instances the delta-regularised solve + refinement can stall short of
+     * the solution of the UNREGULARISED active-set system */
+    sym_mat_vec(&w->P, xx, px);
+    mat_tpose_vec(&Ar, yy, w->tmp_n, 0);
+    double r_d = 0.0, dscale = 0.0, r_p = 0.0;
+    for (ll j = 0; j < n; j++) {
+      double r = fabs(px[j] + w->q[j] + w->tmp_n[j]);
+      double sc = fmax(fabs(px[j]), fmax(fabs(w->q[j]), fabs(w->tmp_n[j])));
+      if (r > r_d) r_d = r;
+      if (sc > dscale) dscale = sc;
+    }
+    for (ll i = 0; i < m; i++) {
+      double v = fmax(fmax(w->l[i] - ax[i], ax[i] - w->u[i]), 0.0);
+      if (v > r_p) r_p = v;
+    }
+    int exact = (r_d <= 1e-8 * (1.0 + dscale)) && (r_p <= 10.0 * tol_p) && r_d == r_d && r_p == r_p;
+    if (!changed) { if (exact) *verified = 1; break; }
   }
   if (ok) {
     for (ll j = 0; j < n; j++) pol_x[j] = xx[j];

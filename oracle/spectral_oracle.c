@@ -826,11 +826,19 @@ int oracle_find_traj_mem(int variant, const OracleProblem *p, int R, const doubl
     /* converged optimum: tighten until the polish is accepted */
     static const double eps_ladder[3] = {1e-6, 1e-8, 1e-10};
     s.polish = 1; s.delta = 1e-9; s.polish_refine_iter = 8; s.max_iter = 50000; s.polish_rounds = 12;
+    double *xt = (double *)calloc((size_t)qp.n + 1, sizeof(double));
+    int have = 0;
     for (int a = 0; a < 3; a++) {
+      OsqpRestateInfo it;
+      memset(&it, 0, sizeof(it));
       s.eps_abs = s.eps_rel = eps_ladder[a];
-      osqp_restate_solve(qp.n, qp.m, qp.P_p, qp.P_i, qp.P_x, qp.q, qp.A_p, qp.A_i, qp.A_x, qp.l, qp.u, &s, x, NULL, &info);
-      if (info.polish_status == 2 || !(info.status == 1 || info.status == 2)) break;
+      osqp_restate_solve(qp.n, qp.m, qp.P_p, qp.P_i, qp.P_x, qp.q, qp.A_p, qp.A_i, qp.A_x, qp.l, qp.u, &s, xt, NULL, &it);
+      const int solved = it.status == 1 || it.status == 2;
+      /* a tighter rung that runs out of iterations does not un-solve the problem: keep the last solved rung */
+      if (solved || !have) { info = it; memcpy(x, xt, sizeof(double) * (size_t)qp.n); have = solved; }
+      if (it.polish_status == 2 || !solved) break;
     }
+    free(xt);
   }
   res->iters = info.iter;
   res->polish_status = info.polish_status;

@@ -501,6 +501,88 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
   io.xv = xv;
 }
 
+// The NCH = 4 form of qpd_block: a thread is (v, h) = quarter row h of G for variable v in S3, one term of the
+// variable's gather in S2 (all lanes busy: the same four-load / four-FMA stream with per-thread coefficients, summed by
+// two butterfly shuffles) and exactly ONE constraint row in S1 (difference row ta < NN, continuity row NN <= ta < ROWS).
+//   h = 0: t_k V0[j] + 5 (V1[j-1] - V1[j]) + sigma x - q      h = 1: 20 (V2[j-2] - 2 V2[j-1] + V2[j])
+//   h = 2: 60 (V3[j-3] - 3 V3[j-2] + 3 V3[j-1] - V3[j])        h = 3: the three continuity rows that touch the variable
+template <int KC, typename SyncFn>
+SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+  using L = QpdLayout<KC>;
+  constexpr int N = L::N, CH = L::CH, TA = L::TA;
+  static_assert(L::NCH == 4 && !L::TWO_SLOTS, "one row per thread");
+  const int v = ta >> 2, h = ta & 3;
+  const bool isg = v < N;
+  const bool isvar = isg && h == 0;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
+  const double *vb = smx + L::O_V + QPD_VB * vk;
+  double *gvp = smx + L::O_GV + (isg ? v : 0);
+  const double *gvh = smx + L::O_GV + CH * h;
+  double *cxp = smx + L::O_C + QPD_CP + (isg ? v : 0);
+  const double *gp0 = vb, *gp1 = vb;
+  double gc0 = 0.0, gc1 = 0.0, gc2 = 0.0, gc3 = 0.0;
+  if (isg) {
+    if (h == 0) { gp0 = vb + QPD_V0 + vj; gp1 = vb + QPD_V1 + vj - 1; gc0 = io.tkv; gc1 = 5.0; gc2 = -5.0; }
+    else if (h == 1) { gp1 = vb + QPD_V2 + vj - 2; gc1 = 20.0; gc2 = -40.0; gc3 = 20.0; }
+    else if (h == 2) { gp0 = vb + QPD_V3 + vj - 3; gp1 = gp0 + 1; gc0 = 60.0; gc1 = -180.0; gc2 = 180.0; gc3 = -60.0; }
+    else {
+      const double *vcf = smx + L::O_VCF + 3 * v;  // continuity gather coefficients (zero for unused segments)
+      gp1 = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1) + QPD_VC; gc1 = vcf[0]; gc2 = vcf[1]; gc3 = vcf[2];
+    }
+  }
+  // the thread's row
+  const bool isj = io.rows[2].meta & 8;
+  const int ri = isj ? 2 : 0;
+  QpdRow r = io.rows[ri];
+  const bool rvalid = r.meta & 8;
+  const int order = r.meta & 3;
+  const double *cp = smx + L::O_C + r.coff;
+  double *vp = smx + L::O_V + r.voff;
+  const QpdLU *lu = (const QpdLU *)(smx + L::O_LU) + ta + (isj ? 2 * TA : 0);
+  const double *cej = smx + L::O_CE + 6 * (isj ? 3 * ((r.meta >> 8) & 0xff) + ((r.meta >> 16) - 18) : 0);
+  double xv = io.xv;
+  const double sigv = io.sigv, qv = io.qv;
+  double G[CH];
+#pragma unroll
+  for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  for (int i = 0; i < n; i++) {
+    {  // S2
+      const double l0 = gp0[0], l1 = gp1[0], l2 = gp1[1], l3 = gp1[2];
+      double p = (gc0 * l0 + gc1 * l1) + (gc2 * l2 + gc3 * l3);
+      p += sigv * xv - qv;  // zero except on the variable thread
+      p += sp_shfl_xor(p, 1);
+      p += sp_shfl_xor(p, 2);
+      if (isvar) *gvp = p;
+    }
+    sync_cta();
+    {  // S3
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int e = 0; e + 3 < CH; e += 4) {
+        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];
+      }
+#pragma unroll
+      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];
+      double xt = (a0 + a1) + (a2 + a3);
+      xt += sp_shfl_xor(xt, 1);
+      xt += sp_shfl_xor(xt, 2);
+      if (isvar) {
+        xv = alpha * xt + (1.0 - alpha) * xv;
+        *cxp = xt;
+      }
+    }
+    sync_cta();
+    if (rvalid) {  // S1
+      const QpdLU b = lu[0];
+      const double zt = isj ? qpd_join_row(cp, cej) : qpd_diff_row(cp, order, r.scale);
+      *vp = qpd_row_update(r, b, zt, alpha);
+    }
+    sync_cta();
+  }
+  io.rows[ri].w = r.w; io.rows[ri].p = r.p;
+  io.xv = xv;
+}
+
 // OSQP's termination test (residuals in the scaled space, scaled_termination = 1), primal-infeasibility
 // certificate and adaptive-rho rule, evaluated CTA-wide = jointly over the s and l problems of the scenario.
 // Called by all threads of the CTA on check iterations.
@@ -697,11 +779,15 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       it_end = nxt < it_end ? nxt : it_end;
     }
     const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
-    if (it_end > it) qpd_block<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
+    if (it_end > it) {
+      if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
+      else qpd_block<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
+    }
     // check iterations keep the old multipliers y = rho (w - clip(w)) for delta y
 #pragma unroll
     for (int r = 0; r < 3; r++) io.yo[r] = io.rows[r].rho * (io.rows[r].w - io.rows[r].p);
-    qpd_block<KC>(io, smx, ta, 1, o.alpha, sync_cta);
+    if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, 1, o.alpha, sync_cta);
+    else qpd_block<KC>(io, smx, ta, 1, o.alpha, sync_cta);
     iters = it_end;
     it = it_end + 1;
     if (!check) continue;

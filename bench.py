@@ -98,6 +98,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _cpu_reference(batch, weights, n_scen, threads):
     """The reference's CPU implementation of the path on `n_scen` scenarios: oracle/_ref (the reference's own
     sources + OSQP restatement) when present, else the plain-C port.  Returns (seconds, kind, result)."""
@@ -105,6 +112,8 @@ def _cpu_reference(batch, weights, n_scen, threads):
     import pyoracle as po
     kind = "reference" if po.have_reference() else "port"
     sub = batch.slice(0, n_scen)
+    # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1, which an OpenMP default would obey
+    threads = threads if threads > 0 else _host_threads()
     t0 = time.perf_counter()
     r = po.solve_batch("cub", sub, weights, mode=0, nthreads=threads, kind=kind)
     return time.perf_counter() - t0, kind, r
@@ -116,7 +125,7 @@ def run_reference(args):
     if rank != 0:
         return
     from spectral_b200.scenarios import GOLDEN_W_CUB, config2
-    cores = os.cpu_count() or 1
+    cores = _host_threads()
     sample = 256
     batch = config2(BATCH)
     times = []
@@ -313,7 +322,7 @@ def run_ours(args):
                                   "unit": "GB/s", "frac": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                                   "traffic": None, "peak_source": peak_src, "ms_per_launch": cor_ms},
             "kernel_ms_per_step": {k: kt[k] / calls for k in ("tables", "corridor", "classify", "qp", "finalize")},
-            "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+            "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": _host_threads(), "kind": kind,
                              "sample": "first %d scenarios of one 1024-scenario batch, reference OSQP settings" % cpu_sample},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk,

@@ -50,6 +50,23 @@ SP_DEV double sp_group_sum(double v, int width) {
   for (int m = width >> 1; m > 0; m >>= 1) v = v + sp_shfl_xor(v, m);
   return v;
 }
+// warp-wide maximum of NON-NEGATIVE doubles (norms): their bit patterns order like unsigned integers, so two integer
+// REDUX steps (high word, then low word among the lanes that hold the winning high word) replace five shuffle rounds of
+// NaN-propagating fmax sequences.  Exact.  A NaN (positive quiet pattern) wins, which makes the caller's `norm < eps`
+// tests fail instead of silently dropping it.
+#ifdef SPECTRAL_CPU_EMU
+SP_DEV double sp_warp_max_nonneg(double v) {
+  for (int m = 16; m > 0; m >>= 1) { const double o = sp_shfl_xor(v, m); v = (o > v || o != o) ? o : v; }
+  return v;
+}
+#else
+SP_DEV double sp_warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(SP_FULL, hi);
+  const unsigned ml = __reduce_max_sync(SP_FULL, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+#endif
 SP_DEV int sp_group_or(int v, int width) {
   for (int m = width >> 1; m > 0; m >>= 1) v = v | sp_shfl_xor_i(v, m);
   return v;

@@ -96,6 +96,32 @@ struct QpdLayout {
   static constexpr int BYTES = TOTAL * 8;
 };
 
+// 16-byte shared-memory load as an ordered (volatile) statement: a run of these is issued back to back, so their
+// latencies overlap instead of each load being consumed before the next one is issued
+SP_DEV void qpd_lds2(const double *p, double &a, double &b) {
+#ifdef SPECTRAL_CPU_EMU
+  a = p[0]; b = p[1];
+#else
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned)__cvta_generic_to_shared(p)));
+#endif
+}
+// Staged loads (a run of loads, a fence, then the arithmetic) need temporaries for everything in flight: they pay where
+// the register budget has room (KC <= 8: 168 registers, measured 14.9 -> 12.5 ms) and spill where it has not (KC = 10 at
+// 128 registers: 9.5 -> 12.2 ms; KC >= 12 at 96 / 80: 8.0 -> 8.9 ms) -- profiles/r1_qpd_staging.md.
+#ifndef QPD_STAGE
+#define QPD_STAGE(KC) ((KC) <= 8)
+#endif
+template <bool ON>
+SP_DEV void qpd_sched_fence_if() {
+#ifndef SPECTRAL_CPU_EMU
+  if (ON) asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
+SP_DEV void qpd_sched_fence() {
+#ifndef SPECTRAL_CPU_EMU
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
 // clip(w, [l, u]) as two compare-selects (fmin/fmax expand to NaN-propagation sequences four times as long)
 SP_DEV double qpd_clip(double w, double l, double u) {
   const double a = w < l ? l : w;
@@ -137,6 +163,7 @@ struct QpdRow {
   int coff;                // offset of the stencil window in C / XR
   int voff;                // offset of this row's value in V
   int meta;                // bits 0-1 difference order, bit 3 valid, bit 4 equality row, bits 8-15 segment, 16.. row in slots (r)
+  double er;               // Ruiz row scaling E_r = sqrt(rho_r c / (rhobar eqfac)): invariant under adaptive rho (checks only)
 };
 
 // Chunk h of row v of G = S^-1: the NCH threads (v, 0..NCH-1), adjacent lanes, run the block forward / backward
@@ -196,24 +223,24 @@ SP_DEV void qpd_inverse_chunk(const double *fs, int v, int h, double *g) {
   }
 }
 
-// CTA-wide reduction of QPD_NRED values: slots 0..8 max, slot 9 sum.  All threads return the result in r[].
+// CTA-wide reduction of QPD_NRED values: slots 0..8 max (of non-negative norms), slot 9 sum.  All threads return the
+// result in r[].  Two levels, both inside a warp: every warp reduces its lanes, lane 0 publishes the ten values, then
+// every warp reduces the per-warp values (lane w reads warp w's) -- no serial loop over the warps, no fmax sequences.
+// The sum is a fixed shuffle tree on both levels, so the result does not depend on scheduling.
 template <typename SyncFn>
 SP_DEV void qpd_reduce(double r[QPD_NRED], double *red, int warp, int lane, int nwarps, SyncFn sync_cta) {
 #pragma unroll
-  for (int i = 0; i < QPD_NRED - 1; i++) r[i] = sp_group_max(r[i], 32);
+  for (int i = 0; i < QPD_NRED - 1; i++) r[i] = sp_warp_max_nonneg(r[i]);
   r[QPD_NRED - 1] = sp_group_sum(r[QPD_NRED - 1], 32);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < QPD_NRED; i++) red[warp * QPD_NRED + i] = r[i];
   }
   sync_cta();
+  const double *mine = red + (lane < nwarps ? lane : 0) * QPD_NRED;
 #pragma unroll
-  for (int i = 0; i < QPD_NRED; i++) r[i] = red[i];
-  for (int w = 1; w < nwarps; w++) {
-#pragma unroll
-    for (int i = 0; i < QPD_NRED - 1; i++) r[i] = fmax(r[i], red[w * QPD_NRED + i]);
-    r[QPD_NRED - 1] += red[w * QPD_NRED + QPD_NRED - 1];
-  }
+  for (int i = 0; i < QPD_NRED - 1; i++) r[i] = sp_warp_max_nonneg(lane < nwarps ? mine[i] : 0.0);
+  r[QPD_NRED - 1] = sp_group_sum(lane < nwarps ? mine[QPD_NRED - 1] : 0.0, 32);
   sync_cta();  // red[] may be reused
 }
 
@@ -362,7 +389,7 @@ SP_DEV_NOINLINE void qpd_build_g(const double *fs, int v, int h, bool isg, doubl
 
 // initial state of a difference-row slot: e = row index in [0, 18 KC) or < 0 (no row)
 template <int KC>
-SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl, const double *lsx, const int *eqa) {
+SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl, const double *lsx, const int *eqa, double c_over_rhobar) {
   using L = QpdLayout<KC>;
   constexpr int STR = L::STR;
   int order = 0, k = 0, i = 0;
@@ -381,26 +408,29 @@ SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl,
   lu.l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
   lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
   r.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
+  r.er = sqrt(r.rho * c_over_rhobar * (eq ? 1e-3 : 1.0));
 }
 
+// max as one compare-select (fmax expands to a NaN-propagation sequence four times as long); a NaN in b is dropped
+SP_DEV double qpd_max(double a, double b) { return b > a ? b : a; }
 // check iterations: delta y of a row -> V, its scaled norm (red_v[7]) and the support-function term (red_v[9])
 SP_DEV void qpd_check_dy(const QpdRow &r, const QpdLU &b, double yo, double *vv, double c_scale, double c_over_rhobar, double *red_v) {
   if (!(r.meta & 8)) return;
   const double dy = r.rho * (r.w - r.p) - yo;
   vv[r.voff] = dy;
   if (r.rho > 0.0) {
-    const double Er = sqrt(r.rho * c_over_rhobar * ((r.meta & 16) ? 1e-3 : 1.0));
-    red_v[7] = fmax(red_v[7], fabs(c_scale * dy / Er));
-    red_v[9] += c_scale * (b.u * fmax(dy, 0.0) + b.l * fmin(dy, 0.0));
+    const double Er = r.er;
+    red_v[7] = qpd_max(red_v[7], fabs(c_scale * dy / Er));
+    red_v[9] += c_scale * (b.u * qpd_max(dy, 0.0) + b.l * (dy < 0.0 ? dy : 0.0));
   }
 }
 // check iterations: primal residual terms of a row, ax = (A x)_row
 SP_DEV void qpd_check_resid(const QpdRow &r, double ax, double c_over_rhobar, double *red_v) {
   if (!(r.meta & 8) || !(r.rho > 0.0)) return;
-  const double Er = sqrt(r.rho * c_over_rhobar * ((r.meta & 16) ? 1e-3 : 1.0));
-  red_v[0] = fmax(red_v[0], Er * fabs(ax - r.p));
-  red_v[2] = fmax(red_v[2], Er * fabs(r.p));
-  red_v[3] = fmax(red_v[3], Er * fabs(ax));
+  const double Er = r.er;
+  red_v[0] = qpd_max(red_v[0], Er * fabs(ax - r.p));
+  red_v[2] = qpd_max(red_v[2], Er * fabs(r.p));
+  red_v[3] = qpd_max(red_v[3], Er * fabs(ax));
 }
 // adaptive rho: keep (z, y), w' = z + y / rho'; publish the new rho in the lane-per-segment RHO slots
 SP_DEV void qpd_rescale_row(QpdRow &r, double ratio, int K, double *ctl_rho, int str) {
@@ -471,16 +501,34 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
 #pragma unroll
   for (int e = 0; e < CH; e++) G[e] = io.G[e];
   for (int i = 0; i < n; i++) {
-    if (isvar) *gvp = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]) + sigv * xv - qv;
+    if (isvar) {  // S2: the 13 loads of the gather in one run, then the arithmetic of qpd_gather
+      const double g0 = vb[QPD_V0 + vj], g1a = vb[QPD_V1 + vj - 1], g1b = vb[QPD_V1 + vj];
+      const double g2a = vb[QPD_V2 + vj - 2], g2b = vb[QPD_V2 + vj - 1], g2c = vb[QPD_V2 + vj];
+      const double g3a = vb[QPD_V3 + vj - 3], g3b = vb[QPD_V3 + vj - 2], g3c = vb[QPD_V3 + vj - 1], g3d = vb[QPD_V3 + vj];
+      const double c0 = vkk[QPD_VC], c1 = vkk[QPD_VC + 1], c2 = vkk[QPD_VC + 2];
+      const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];
+      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      double g = tkv * g0;
+      g += 5.0 * (g1a - g1b);
+      g += 20.0 * ((g2a - g2b) - (g2b - g2c));
+      g += 60.0 * ((g3a - g3d) + 3.0 * (g3c - g3b));
+      g += f0 * c0 + f1 * c1 + f2 * c2;
+      *gvp = g + sigv * xv - qv;
+    }
     sync_cta();
     {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      static_assert(CH % 2 == 0, "g chunks are loaded in 16-byte pairs");
+      double gl[CH];
+#pragma unroll
+      for (int e = 0; e < CH; e += 2) qpd_lds2(gvh + e, gl[e], gl[e + 1]);
+      qpd_sched_fence_if<QPD_STAGE(KC)>();  // keeps the loads above in one back-to-back run (ptxas otherwise consumes each one before the next)
 #pragma unroll
       for (int e = 0; e + 3 < CH; e += 4) {
-        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];
+        a0 += G[e] * gl[e]; a1 += G[e + 1] * gl[e + 1]; a2 += G[e + 2] * gl[e + 2]; a3 += G[e + 3] * gl[e + 3];
       }
 #pragma unroll
-      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];
+      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gl[e];
       double xt = (a0 + a1) + (a2 + a3);
       xt += sp_shfl_xor(xt, 1);
       if (L::NCH == 4) xt += sp_shfl_xor(xt, 2);
@@ -490,9 +538,32 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
       }
     }
     sync_cta();
-    if (va) *vpa = qpd_row_update(ra, lua[0], qpd_diff_row(cpa, oa, ra.scale), alpha);
-    if (vbb) *vpb = qpd_row_update(rb, lub[0], qpd_diff_row(cpb, ob, rb.scale), alpha);
-    if (vjj) *vpj = qpd_row_update(rj, luj[0], qpd_join_row(cpj, cej), alpha);
+    // S1: the two row slots of a thread as one straight-line stream (loads of both first, then both updates), chosen by a
+    // warp-uniform branch: threads >= T0 own two difference rows, threads < T0 a difference row and a continuity row.
+    // Slots without a row compute on valid dummy addresses and skip the store.
+    if (L::TWO_SLOTS && ta >= L::T0) {
+      const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
+      const double b0 = cpb[0], b1 = cpb[1], b2 = cpb[2], b3 = cpb[3];
+      const QpdLU la = lua[0], lb = lub[0];
+      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      const double wa[4] = {a0, a1, a2, a3}, wb[4] = {b0, b1, b2, b3};
+      const double za = qpd_diff_row(wa, oa, ra.scale), zb = qpd_diff_row(wb, ob, rb.scale);
+      const double ua = qpd_row_update(ra, la, za, alpha), ub = qpd_row_update(rb, lb, zb, alpha);
+      if (va) *vpa = ua;
+      if (vbb) *vpb = ub;
+    } else {
+      const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
+      const double j0 = cpj[0], j1 = cpj[1], j2 = cpj[2], j3 = cpj[3], j4 = cpj[4], j5 = cpj[5];
+      const double e0 = cej[0], e1 = cej[1], e2 = cej[2], e3 = cej[3], e4 = cej[4], e5 = cej[5];
+      const QpdLU la = lua[0], lj = luj[0];
+      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      const double wa[4] = {a0, a1, a2, a3};
+      const double za = qpd_diff_row(wa, oa, ra.scale);
+      const double zj = (e0 * j0 + e1 * j1) + (e2 * j2 + e3 * j3) + (e4 * j4 + e5 * j5);
+      const double ua = qpd_row_update(ra, la, za, alpha), uj = qpd_row_update(rj, lj, zj, alpha);
+      if (va) *vpa = ua;
+      if (vjj) *vpj = uj;
+    }
     sync_cta();
   }
   io.rows[0].w = ra.w; io.rows[0].p = ra.p;
@@ -557,12 +628,16 @@ SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
     sync_cta();
     {  // S3
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      static_assert(CH % 2 == 0, "g chunks are loaded in 16-byte pairs");
+      double gl[CH];
+#pragma unroll
+      for (int e = 0; e < CH; e += 2) qpd_lds2(gvh + e, gl[e], gl[e + 1]);
 #pragma unroll
       for (int e = 0; e + 3 < CH; e += 4) {
-        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];
+        a0 += G[e] * gl[e]; a1 += G[e + 1] * gl[e + 1]; a2 += G[e + 2] * gl[e + 2]; a3 += G[e + 3] * gl[e + 3];
       }
 #pragma unroll
-      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gvh[e];
+      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gl[e];
       double xt = (a0 + a1) + (a2 + a3);
       xt += sp_shfl_xor(xt, 1);
       xt += sp_shfl_xor(xt, 2);
@@ -730,8 +805,8 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       ea = ta < L::NN ? ta : -1; eb = -1;
       ej = (ta >= L::NN && ta < L::ROWS) ? ta - L::NN : -1;
     }
-    qpd_init_diff<KC>(io.rows[0], lua[0], ea, K, ctl, lsx, eqm + axis * LPA);
-    qpd_init_diff<KC>(io.rows[1], lub[0], eb, K, ctl, lsx, eqm + axis * LPA);
+    qpd_init_diff<KC>(io.rows[0], lua[0], ea, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+    qpd_init_diff<KC>(io.rows[1], lub[0], eb, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
     QpdRow &rj = io.rows[2];
     const bool jvalid = ej >= 0;
     const int k = jvalid ? ej / 3 : 0, rr = jvalid ? ej - 3 * k : 0;
@@ -747,6 +822,7 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     luj[0].l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
     luj[0].u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
     rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
+    rj.er = sqrt(rj.rho * (c_scale / rhobar) * (eq ? 1e-3 : 1.0));
   }
   // G thread (v, h); the h = 0 thread is the variable thread of v
   const int v = ta / L::NCH, h = ta % L::NCH;

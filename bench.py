@@ -258,26 +258,44 @@ def run_ours(args):
     ms_max = float(t_ms.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- end to end: host (pinned) buffers through spectral_solve_batch, H2D + kernels + D2H per step
-    pin = {k: torch.from_numpy(a).pin_memory() for k, a in host.items()}
-    pin_np = {k: t.numpy() for k, t in pin.items()}
+    # ---- end to end: HOST buffers through the public host API (spectral_solve_batch_async / spectral_wait), the
+    #      H2D copy of every step's inputs from page-locked memory, the kernels and the D2H copy of every step's outputs
+    #      inside the timed region; NS planners (handle + stream each) are cycled so that the copies and the ragged tail
+    #      of one step overlap the kernels of the next -- the way a sweep driver calls the library
     from spectral_b200.wire import ScenarioBatch
 
     def host_batch(i):
         s = i % POOL
-        return ScenarioBatch(N, R, delta, *[pin_np[k][s * B:(s + 1) * B] for k in names])
+        return ScenarioBatch(N, R, delta, *[host[k][s * B:(s + 1) * B] for k in names])
 
     hb = [host_batch(i) for i in range(POOL)]
     w_host = np.array(GOLDEN_W_CUB)
-    for i in range(max(3, args.warmup)):
-        res = planner.solve("cub", hb[i % POOL], w_host)
+    # every planner owns page-locked staging buffers; a step's inputs are copied into them (host memcpy, timed) and
+    # from there to the device
+    best = []
+    for i in range(max(3, args.warmup, NS)):
+        pl = planners[i % NS]
+        if getattr(pl, "_pending", None) is not None:
+            pl.wait()
+        pl.solve_async("cub", hb[i % POOL], w_host)
+    for pl in planners:
+        if getattr(pl, "_pending", None) is not None:
+            pl.wait()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = planner.solve("cub", hb[(args.warmup + i) % POOL], w_host)
-        _ = float(res.a_cost.min())
+        pl = planners[i % NS]
+        if getattr(pl, "_pending", None) is not None:
+            res = pl.wait()
+            best.append(float(res.a_cost.min()))  # the step's result is read on the host
+        pl.solve_async("cub", hb[(args.warmup + i) % POOL], w_host)
+    for pl in planners:
+        if getattr(pl, "_pending", None) is not None:
+            res = pl.wait()
+            best.append(float(res.a_cost.min()))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert len(best) == args.steps
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)

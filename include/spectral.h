@@ -24,6 +24,8 @@
 #ifndef SPECTRAL_H
 #define SPECTRAL_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -135,6 +137,19 @@ const char *spectral_last_error(const spectral_handle_t *h);
 int spectral_solve_batch(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
                          const SpectralInputs *host_in, const SpectralOptions *opt,
                          SpectralOutputs *host_out);
+
+/* The same, split for pipelining: _async enqueues the copies and kernels on the handle's own stream and returns;
+ * spectral_wait() blocks until the outputs have landed.  host_in / host_out buffers must stay valid (and host_out
+ * untouched) until then; with page-locked buffers (spectral_host_alloc) the copies overlap the kernels of other
+ * handles, which is how a caller keeps the GPU full at small batch sizes: a few handles, round robin.
+ * At most one batch in flight per handle.  (The reference's find_traj is synchronous: trp_wrapper.cpp:16-306.) */
+int spectral_solve_batch_async(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                               const SpectralInputs *host_in, const SpectralOptions *opt,
+                               SpectralOutputs *host_out);
+int spectral_wait(spectral_handle_t *h);
+/* Page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost). */
+int spectral_host_alloc(void **ptr, size_t bytes);
+int spectral_host_free(void *ptr);
 
 /* Device buffers (already resident in HBM): enqueues on `cuda_stream` (a cudaStream_t, may be NULL)
  * and returns without synchronising. */

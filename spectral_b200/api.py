@@ -97,7 +97,10 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_last_error.argtypes = [ctypes.c_void_p]
     lib.spectral_last_error.restype = ctypes.c_char_p
     lib.spectral_default_options.argtypes = [ctypes.POINTER(SpectralOptions)]
-    for fn in (lib.spectral_solve_batch,):
+    lib.spectral_wait.argtypes = [ctypes.c_void_p]
+    lib.spectral_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    lib.spectral_host_free.argtypes = [ctypes.c_void_p]
+    for fn in (lib.spectral_solve_batch, lib.spectral_solve_batch_async):
         fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                        ctypes.POINTER(SpectralInputs), ctypes.POINTER(SpectralOptions), ctypes.POINTER(SpectralOutputs)]
     lib.spectral_solve_batch_device.argtypes = lib.spectral_solve_batch.argtypes + [ctypes.c_void_p]
@@ -167,6 +170,11 @@ class SpectralPlanner:
 
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_pending", None) is not None:
+                self._lib.spectral_wait(self._h)
+                self._pending = None
+            for _, ptr in self.__dict__.pop("_pin", {}).values():
+                self._lib.spectral_host_free(ptr)
             self._lib.spectral_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -202,6 +210,73 @@ class SpectralPlanner:
                                                    float(batch.delta_t), ctypes.byref(inp),
                                                    ctypes.byref(options) if options is not None else None,
                                                    ctypes.byref(out)))
+        return res
+
+    # ---- pipelined host path: page-locked buffers owned by the planner, one batch in flight per planner
+    def _pinned(self, key, shape, dtype):
+        """A page-locked numpy array (cudaHostAlloc through the C-ABI), cached per (name, shape)."""
+        cache = self.__dict__.setdefault("_pin", {})
+        k = (key, tuple(shape), np.dtype(dtype).str)
+        if k not in cache:
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            ptr = ctypes.c_void_p()
+            self._check(self._lib.spectral_host_alloc(ctypes.byref(ptr), max(nbytes, 1)))
+            buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr.value)
+            cache[k] = (np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), ptr)
+        return cache[k][0]
+
+    def solve_async(self, variant, batch: ScenarioBatch, weights: Sequence[float],
+                    options: Optional[SpectralOptions] = None) -> None:
+        """Enqueue one batch (H2D copies, kernels, D2H copies) on this planner's stream and return; `wait()` returns the
+        result.  Inputs are staged into page-locked buffers unless they already are this planner's (see `pinned_inputs`).
+        A caller keeps the GPU full by cycling over a few planners."""
+        if getattr(self, "_pending", None) is not None:
+            raise RuntimeError("a batch is already in flight on this planner: call wait() first")
+        B, km = batch.batch, self.k_max
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+        if w.shape not in ((10,), (B, 10)):
+            raise ValueError("weights must have shape (10,) or (B, 10)")
+        names = ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars")
+        staged = []
+        for name, a in zip(names, batch.arrays()):
+            pin = self._pinned("in_" + name, a.shape, np.float64)
+            if a is not pin:
+                np.copyto(pin, a)
+            staged.append(pin)
+        wp = self._pinned("in_w", w.shape, np.float64)
+        np.copyto(wp, w)
+        inp = SpectralInputs(*[_d(a) for a in staged], _d(wp), 0 if w.ndim == 1 else 1)
+        res = BatchResult(self._pinned("K", (B,), np.int32), self._pinned("segs", (B, km), CUBE_DTYPE),
+                          self._pinned("ctrl", (B, 12 * km), np.float64), self._pinned("obj", (B,), np.float64),
+                          self._pinned("a_cost", (B,), np.float64), self._pinned("status", (B,), np.int32),
+                          self._pinned("iters", (B,), np.int32), self._pinned("flags", (B,), np.int32),
+                          self._pinned("npts", (B,), np.int32), None, None)
+        out = SpectralOutputs(_i(res.K), res.segs.ctypes.data_as(ctypes.c_void_p), _d(res.ctrl), _d(res.obj),
+                              _d(res.a_cost), _i(res.status), _i(res.iters), _i(res.flags), _i(res.npts), None, 0, None)
+        self._check(self._lib.spectral_solve_batch_async(self._h, VARIANT_ID[variant], B, batch.n_knots, batch.n_regions,
+                                                         float(batch.delta_t), ctypes.byref(inp),
+                                                         ctypes.byref(options) if options is not None else None,
+                                                         ctypes.byref(out)))
+        self._pending = (res, inp, out, staged, wp)  # keeps the argument structs alive
+
+    def pinned_inputs(self, batch: ScenarioBatch) -> ScenarioBatch:
+        """Copy of `batch` living in this planner's page-locked input buffers: passing it to solve_async skips the staging copy."""
+        names = ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars")
+        arrs = []
+        for name, a in zip(names, batch.arrays()):
+            pin = self._pinned("in_" + name, a.shape, np.float64)
+            np.copyto(pin, a)
+            arrs.append(pin)
+        return ScenarioBatch(batch.n_knots, batch.n_regions, batch.delta_t, *arrs)
+
+    def wait(self) -> BatchResult:
+        """Block until the batch enqueued by solve_async has landed; the arrays are views of the planner's page-locked
+        output buffers and are overwritten by the next solve_async on this planner."""
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("nothing in flight")
+        self._check(self._lib.spectral_wait(self._h))
+        res = self._pending[0]
+        self._pending = None
         return res
 
     # ---- resident path: torch CUDA tensors (float64 / int32), enqueued on the current stream

@@ -438,8 +438,8 @@ static int ensure(spectral_handle *h, T **p, size_t *cur, size_t need) {
   return SPECTRAL_SUCCESS;
 }
 
-extern "C" int spectral_solve_batch(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
-                                    const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
+extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                          const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
   if (!h || !hin || !hout) return SPECTRAL_ERR_INVALID;
   if (B <= 0 || B > h->max_batch) return fail(h, SPECTRAL_ERR_CAPACITY, "batch exceeds max_batch");
   if (!hout->K || !hout->status) return fail(h, SPECTRAL_ERR_INVALID, "K and status outputs are required");
@@ -495,8 +495,31 @@ extern "C" int spectral_solve_batch(spectral_handle_t *h, int variant, int B, in
   D2H(hout->samples, h->d_samples, b * (size_t)hout->samples_cap * 48);
   D2H(hout->lu, h->d_lu, b * 2 * km * QP_ROWS * 16);
 #undef D2H
-  CK(cudaStreamSynchronize(st));
   return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_wait(spectral_handle_t *h) {
+  if (!h) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_solve_batch(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                    const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
+  const int rc = spectral_solve_batch_async(h, variant, B, N, R, delta_t, hin, opt, hout);
+  if (rc) return rc;
+  return spectral_wait(h);
+}
+
+extern "C" int spectral_host_alloc(void **p, size_t bytes) {
+  if (!p) return SPECTRAL_ERR_INVALID;
+  *p = nullptr;
+  return cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? SPECTRAL_SUCCESS : SPECTRAL_ERR_CUDA;
+}
+extern "C" int spectral_host_free(void *p) {
+  if (!p) return SPECTRAL_SUCCESS;
+  return cudaFreeHost(p) == cudaSuccess ? SPECTRAL_SUCCESS : SPECTRAL_ERR_CUDA;
 }
 
 extern "C" int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,

@@ -109,7 +109,10 @@ SP_DEV void qpd_lds2(const double *p, double &a, double &b) {
 // the register budget has room (KC <= 8: 168 registers, measured 14.9 -> 12.5 ms) and spill where it has not (KC = 10 at
 // 128 registers: 9.5 -> 12.2 ms; KC >= 12 at 96 / 80: 8.0 -> 8.9 ms) -- profiles/r1_qpd_staging.md.
 #ifndef QPD_STAGE
-#define QPD_STAGE(KC) ((KC) <= 8)
+#define QPD_STAGE(KC) ((KC) <= 8)      // S3: the whole g chunk in flight (CH doubles of temporaries)
+#endif
+#ifndef QPD_STAGE_ROWS
+#define QPD_STAGE_ROWS(KC) ((KC) <= 8)   // S2 / S1: 13 - 18 doubles of temporaries (KC = 10 at 128 registers: 9.5 -> 10.6 ms)
 #endif
 template <bool ON>
 SP_DEV void qpd_sched_fence_if() {
@@ -489,12 +492,16 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
   double *cxp = cx + QPD_CP + (isg ? v : 0);
   double *vv = smx + L::O_V;
   const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
-  QpdRow ra = io.rows[0], rb = io.rows[1], rj = io.rows[2];
-  const double *cej = smx + L::O_CE + 6 * ((rj.meta & 8) ? 3 * ((rj.meta >> 8) & 0xff) + ((rj.meta >> 16) - 18) : 0);
-  const double *cpa = cx + ra.coff, *cpb = cx + rb.coff, *cpj = cx + rj.coff;  // stencil windows of the row slots
-  double *vpa = vv + ra.voff, *vpb = vv + rb.voff, *vpj = vv + rj.voff;        // their V entries
-  const bool va = ra.meta & 8, vbb = L::TWO_SLOTS && (rb.meta & 8), vjj = rj.meta & 8;
-  const int oa = ra.meta & 3, ob = rb.meta & 3;
+  // second slot of the thread: difference row B (threads >= T0) or continuity row J (threads < T0), never both
+  const bool second_is_b = L::TWO_SLOTS && ta >= L::T0;
+  const int i2 = second_is_b ? 1 : 2;
+  QpdRow ra = io.rows[0], r2 = io.rows[i2];
+  const double *cej = smx + L::O_CE + 6 * ((!second_is_b && (r2.meta & 8)) ? 3 * ((r2.meta >> 8) & 0xff) + ((r2.meta >> 16) - 18) : 0);
+  const double *cpa = cx + ra.coff, *cp2 = cx + r2.coff;  // stencil windows of the row slots
+  double *vpa = vv + ra.voff, *vp2 = vv + r2.voff;        // their V entries
+  const QpdLU *lu2 = second_is_b ? lub : luj;
+  const bool va = ra.meta & 8, v2 = r2.meta & 8;
+  const int oa = ra.meta & 3, ob = r2.meta & 3;
   double xv = io.xv;
   const double sigv = io.sigv, qv = io.qv, tkv = io.tkv;
   double G[CH];
@@ -507,7 +514,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
       const double g3a = vb[QPD_V3 + vj - 3], g3b = vb[QPD_V3 + vj - 2], g3c = vb[QPD_V3 + vj - 1], g3d = vb[QPD_V3 + vj];
       const double c0 = vkk[QPD_VC], c1 = vkk[QPD_VC + 1], c2 = vkk[QPD_VC + 2];
       const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];
-      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       double g = tkv * g0;
       g += 5.0 * (g1a - g1b);
       g += 20.0 * ((g2a - g2b) - (g2b - g2c));
@@ -541,34 +548,33 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
     // S1: the two row slots of a thread as one straight-line stream (loads of both first, then both updates), chosen by a
     // warp-uniform branch: threads >= T0 own two difference rows, threads < T0 a difference row and a continuity row.
     // Slots without a row compute on valid dummy addresses and skip the store.
-    if (L::TWO_SLOTS && ta >= L::T0) {
+    if (second_is_b) {
       const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
-      const double b0 = cpb[0], b1 = cpb[1], b2 = cpb[2], b3 = cpb[3];
-      const QpdLU la = lua[0], lb = lub[0];
-      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      const double b0 = cp2[0], b1 = cp2[1], b2 = cp2[2], b3 = cp2[3];
+      const QpdLU la = lua[0], lb = lu2[0];
+      qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       const double wa[4] = {a0, a1, a2, a3}, wb[4] = {b0, b1, b2, b3};
-      const double za = qpd_diff_row(wa, oa, ra.scale), zb = qpd_diff_row(wb, ob, rb.scale);
-      const double ua = qpd_row_update(ra, la, za, alpha), ub = qpd_row_update(rb, lb, zb, alpha);
+      const double za = qpd_diff_row(wa, oa, ra.scale), zb = qpd_diff_row(wb, ob, r2.scale);
+      const double ua = qpd_row_update(ra, la, za, alpha), ub = qpd_row_update(r2, lb, zb, alpha);
       if (va) *vpa = ua;
-      if (vbb) *vpb = ub;
+      if (v2) *vp2 = ub;
     } else {
       const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
-      const double j0 = cpj[0], j1 = cpj[1], j2 = cpj[2], j3 = cpj[3], j4 = cpj[4], j5 = cpj[5];
+      const double j0 = cp2[0], j1 = cp2[1], j2 = cp2[2], j3 = cp2[3], j4 = cp2[4], j5 = cp2[5];
       const double e0 = cej[0], e1 = cej[1], e2 = cej[2], e3 = cej[3], e4 = cej[4], e5 = cej[5];
-      const QpdLU la = lua[0], lj = luj[0];
-      qpd_sched_fence_if<QPD_STAGE(KC)>();
+      const QpdLU la = lua[0], lj = lu2[0];
+      qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       const double wa[4] = {a0, a1, a2, a3};
       const double za = qpd_diff_row(wa, oa, ra.scale);
       const double zj = (e0 * j0 + e1 * j1) + (e2 * j2 + e3 * j3) + (e4 * j4 + e5 * j5);
-      const double ua = qpd_row_update(ra, la, za, alpha), uj = qpd_row_update(rj, lj, zj, alpha);
+      const double ua = qpd_row_update(ra, la, za, alpha), uj = qpd_row_update(r2, lj, zj, alpha);
       if (va) *vpa = ua;
-      if (vjj) *vpj = uj;
+      if (v2) *vp2 = uj;
     }
     sync_cta();
   }
   io.rows[0].w = ra.w; io.rows[0].p = ra.p;
-  io.rows[1].w = rb.w; io.rows[1].p = rb.p;
-  io.rows[2].w = rj.w; io.rows[2].p = rj.p;
+  io.rows[i2].w = r2.w; io.rows[i2].p = r2.p;
   io.xv = xv;
 }
 

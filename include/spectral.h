@@ -122,6 +122,15 @@ typedef struct {
   double polish_delta;   /* 1e-6: regularisation of the active rows (OSQP's delta) */
   int polish_refine_iter;/* 4 */
   int polish_rounds;     /* 8: active-set correction rounds; a round that changes nothing verifies the KKT conditions */
+  int infeasibility_precheck; /* 0 (default: every scenario goes through the reference's OSQP iteration).  1: scenarios whose
+                           corridor is PROVABLY empty -- a constraint row with l > u, consecutive segments whose position
+                           intervals do not meet at the joint (rows 5 of segment k and 0 of k+1 share t_k c_k5 = t_k+1 c_k+1,0,
+                           solve_3d.cc:918-925), or an initial state outside the first segment's position / velocity /
+                           acceleration rows (solve_3d.cc:896-912) -- fail at once instead of after up to max_iter ADMM
+                           iterations.  Sound (necessary conditions of feasibility); not what the reference does: on such
+                           problems its OSQP either certifies infeasibility late or stops at max_iter, sometimes with the
+                           status "solved inaccurate" and a constraint-violating trajectory. */
+  double precheck_margin; /* 1e-3: an interval gap must exceed this to count */
 } SpectralOptions;
 
 typedef struct spectral_handle spectral_handle_t;

@@ -63,7 +63,8 @@ class SpectralOptions(ctypes.Structure):
                 ("alpha", ctypes.c_double), ("scaling", ctypes.c_int), ("check_termination", ctypes.c_int),
                 ("adaptive_rho_interval", ctypes.c_int), ("adaptive_rho_tolerance", ctypes.c_double),
                 ("polish", ctypes.c_int), ("polish_delta", ctypes.c_double), ("polish_refine_iter", ctypes.c_int),
-                ("polish_rounds", ctypes.c_int)]
+                ("polish_rounds", ctypes.c_int), ("infeasibility_precheck", ctypes.c_int),
+                ("precheck_margin", ctypes.c_double)]
 
 
 class Params(ctypes.Structure):

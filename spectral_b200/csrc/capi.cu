@@ -219,6 +219,7 @@ extern "C" void spectral_default_options(SpectralOptions *o) {
   o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
   o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
   o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
+  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3;
 }
 
 extern "C" const char *spectral_last_error(const spectral_handle_t *h) { return h ? h->err.c_str() : "null handle"; }
@@ -385,6 +386,7 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   qa.opt.eps_abs = opt.eps_abs; qa.opt.eps_rel = opt.eps_rel; qa.opt.eps_pinf = opt.eps_prim_inf; qa.opt.rho0 = opt.rho;
   qa.opt.sigma = opt.sigma; qa.opt.alpha = opt.alpha; qa.opt.adapt_tol = opt.adaptive_rho_tolerance;
   qa.opt.polish_delta = opt.polish_delta; qa.opt.polish_rounds = opt.polish_rounds;
+  qa.opt.precheck = opt.infeasibility_precheck; qa.opt.precheck_margin = opt.precheck_margin;
   qa.ctrl = out->ctrl; qa.axis_status = h->axis_status; qa.axis_iters = h->axis_iters; qa.axis_polished = h->axis_polished;
   qa.axis_obj = h->axis_obj; qa.lu = out->lu;
   // the solver classes are independent: fork them onto side streams, join before K5

@@ -95,6 +95,6 @@ SP_DEV int sp_group_max_i(int v, int width) {
 #define SP_INVM1_5 0x1.0p+0
 
 struct SpOptionsDev {
-  int max_iter, scaling, check_every, adapt_every, polish, polish_refine, polish_rounds;
-  double eps_abs, eps_rel, eps_pinf, rho0, sigma, alpha, adapt_tol, polish_delta;
+  int max_iter, scaling, check_every, adapt_every, polish, polish_refine, polish_rounds, precheck;
+  double eps_abs, eps_rel, eps_pinf, rho0, sigma, alpha, adapt_tol, polish_delta, precheck_margin;
 };

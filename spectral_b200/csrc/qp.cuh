@@ -427,6 +427,7 @@ struct QpLane {
   double q[6], sig[6], cD[6];
   double c, rhobar;
   unsigned eqmask;
+  int pre;  // interval pre-check: the scenario's corridor is provably empty (SpectralOptions::infeasibility_precheck)
 };
 
 // K3 + Ruiz equilibration + per-row rho: fills the shared-memory slots L, U, W (= 0), P, RHO of this
@@ -524,6 +525,31 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
     lo[20] = hi[20] = rn_mul(ini[2], t);
   } else {
     lo[18] = hi[18] = 0.0; lo[19] = hi[19] = 0.0; lo[20] = hi[20] = 0.0;
+  }
+  // optional interval pre-check (include/spectral.h: infeasibility_precheck): necessary conditions of feasibility on the
+  // raw rows -- no row with l > u; the position intervals of consecutive segments meet at their joint (row 5 of segment
+  // k - 1 and row 0 of segment k bound the same quantity, t_{k-1} c_{k-1,5} = t_k c_{k,0}); the initial state lies inside
+  // the first segment's position / velocity / acceleration rows (rows 18..20 are equalities on the expressions of rows
+  // 0, 6, 11).  OR-ed over the JW lanes that form one OSQP instance.
+  int pre = 0;
+  if (o.precheck) {
+    const double mg = o.precheck_margin;
+    bool bad = false;
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 18; r++) bad = bad || (lo[r] > hi[r] + mg);
+    }
+    const double plo = sp_shfl_up(lo[5], 1, LPA), phi = sp_shfl_up(hi[5], 1, LPA);
+    if (active && !first) {
+      const double jl = lo[0] > plo ? lo[0] : plo, jh = hi[0] < phi ? hi[0] : phi;
+      bad = bad || (jl > jh + mg);
+    }
+    if (active && first) {
+      bad = bad || (lo[18] > hi[0] + mg) || (lo[18] < lo[0] - mg);
+      bad = bad || (lo[19] > hi[6] + mg) || (lo[19] < lo[6] - mg);
+      bad = bad || (lo[20] > hi[11] + mg) || (lo[20] < lo[11] - mg);
+    }
+    pre = sp_group_or(bad ? 1 : 0, JW);
   }
   if (a.lu != nullptr && active) {
     double *dst = a.lu + (((size_t)b * 2 + axis) * a.k_max + seg) * QP_ROWS * 2;
@@ -670,7 +696,7 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
 
   Q.b = b; Q.axis = axis; Q.K = K; Q.seg = seg; Q.kmaxw = kmaxw;
   Q.have = have; Q.active = active; Q.first = first; Q.last = last;
-  Q.t = t; Q.tp = tp; Q.tn = tn; Q.c = c; Q.rhobar = rhobar; Q.eqmask = eqmask;
+  Q.t = t; Q.tp = tp; Q.tn = tn; Q.c = c; Q.rhobar = rhobar; Q.eqmask = eqmask; Q.pre = pre;
 #pragma unroll
   for (int j = 0; j < 6; j++) { Q.q[j] = q[j]; Q.sig[j] = sig[j]; Q.cD[j] = cD[j]; }
 }
@@ -699,7 +725,7 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
 #pragma unroll
   for (int j = 0; j < 6; j++) x[j] = 0.0;
   state = (have && K > 0) ? QP_RUNNING : QP_ST_MAXITER;
-  if (bad) state = QP_ST_INFEASIBLE;
+  if (bad || Q.pre) state = QP_ST_INFEASIBLE;
   iters = 0;
   const double alpha = o.alpha;
 

@@ -282,7 +282,7 @@ SP_DEV void qpd_load_lane(QpLane &Q, const QpArgs &a, int ap, int seg, const dou
   Q.t = d[0]; Q.tp = d[1]; Q.tn = d[2];
 #pragma unroll
   for (int j = 0; j < 6; j++) { Q.q[j] = d[3 + j]; Q.sig[j] = d[9 + j]; Q.cD[j] = d[15 + j]; }
-  Q.c = c; Q.rhobar = rhobar; Q.eqmask = (unsigned)eq[seg];
+  Q.c = c; Q.rhobar = rhobar; Q.eqmask = (unsigned)eq[seg]; Q.pre = 0;
 }
 
 // warp 0: K3 assembly, Ruiz scaling, per-row rho, stencil tables, first factorisation.
@@ -321,7 +321,7 @@ SP_DEV_NOINLINE void qpd_control_setup(const QpArgs &a, int slot, int lane, doub
         }
     }
     const int bad = qpd_refactor<KC>(smc, cfs, Q, creal);
-    if (bad) state = QP_ST_INFEASIBLE;
+    if (bad || Q.pre) state = QP_ST_INFEASIBLE;  // Q.pre of lane 0 = OR over both axes of the scenario
     if (lane == 0) { red[0] = Q.c; red[1] = (double)state; }
   }
 }
@@ -507,7 +507,9 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
   double G[CH];
 #pragma unroll
   for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  double yoa = 0.0, yo2 = 0.0;
   for (int i = 0; i < n; i++) {
+    if (i == n - 1) { yoa = ra.rho * (ra.w - ra.p); yo2 = r2.rho * (r2.w - r2.p); }
     if (isvar) {  // S2: the 13 loads of the gather in one run, then the arithmetic of qpd_gather
       const double g0 = vb[QPD_V0 + vj], g1a = vb[QPD_V1 + vj - 1], g1b = vb[QPD_V1 + vj];
       const double g2a = vb[QPD_V2 + vj - 2], g2b = vb[QPD_V2 + vj - 1], g2c = vb[QPD_V2 + vj];
@@ -575,6 +577,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
   }
   io.rows[0].w = ra.w; io.rows[0].p = ra.p;
   io.rows[i2].w = r2.w; io.rows[i2].p = r2.p;
+  io.yo[0] = yoa; io.yo[1] = 0.0; io.yo[2] = 0.0; io.yo[i2] = yo2;
   io.xv = xv;
 }
 
@@ -622,7 +625,9 @@ SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
   double G[CH];
 #pragma unroll
   for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  double yo = 0.0;
   for (int i = 0; i < n; i++) {
+    if (i == n - 1) yo = r.rho * (r.w - r.p);
     {  // S2
       const double l0 = gp0[0], l1 = gp1[0], l2 = gp1[1], l3 = gp1[2];
       double p = (gc0 * l0 + gc1 * l1) + (gc2 * l2 + gc3 * l3);
@@ -661,6 +666,7 @@ SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
     sync_cta();
   }
   io.rows[ri].w = r.w; io.rows[ri].p = r.p;
+  io.yo[0] = 0.0; io.yo[1] = 0.0; io.yo[2] = 0.0; io.yo[ri] = yo;
   io.xv = xv;
 }
 
@@ -861,15 +867,10 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       it_end = nxt < it_end ? nxt : it_end;
     }
     const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
-    if (it_end > it) {
-      if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
-      else qpd_block<KC>(io, smx, ta, it_end - it, o.alpha, sync_cta);
-    }
-    // check iterations keep the old multipliers y = rho (w - clip(w)) for delta y
-#pragma unroll
-    for (int r = 0; r < 3; r++) io.yo[r] = io.rows[r].rho * (io.rows[r].w - io.rows[r].p);
-    if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, 1, o.alpha, sync_cta);
-    else qpd_block<KC>(io, smx, ta, 1, o.alpha, sync_cta);
+    // one out-of-line call per check interval; before its LAST iteration the block captures the multipliers
+    // y = rho (w - clip(w)) of the thread's rows (io.yo) for the delta y of the check
+    if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
+    else qpd_block<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     iters = it_end;
     it = it_end + 1;
     if (!check) continue;

@@ -240,6 +240,33 @@ def test_device_resident_path_and_argmin(planner):
     assert int(best_idx.item()) == 1000 + j and best_cost.item() == host.a_cost[j]
 
 
+def test_infeasibility_precheck_is_sound(planner):
+    """Option infeasibility_precheck: every scenario it fails early is one the CONVERGED oracle fails too (and never one
+    whose solved class the reference pins); every other scenario is bit-identical to the run without the option."""
+    batch = config2(1024)
+    off = planner.solve("cub", batch, GOLDEN_W_CUB)
+    on = planner.solve("cub", batch, GOLDEN_W_CUB, options=api.default_options(infeasibility_precheck=1))
+    early = (on.status == api.FAIL_SOLVER) & (on.iters == 0) & (off.iters > 0)
+    assert early.sum() > 100, "config 2 holds hundreds of provably empty corridors"
+    ref, ref0 = H.oracle_pair("cub", batch, GOLDEN_W_CUB)
+    # the converged oracle never reaches an accurate optimum on them (a handful end as "solved inaccurate" at its
+    # iteration cap: ADMM hovering at a small residual of an infeasible problem), none carries a KKT proof ...
+    assert np.all(ref["status"][early] != 0) and not (ref["polish"][early] == 2).any(), \
+        "pre-check failed a scenario that has a converged optimum"
+    assert (ref["status"][early] > 1).mean() > 0.98
+    # ... and an independent solver (HiGHS on the reference-assembled QP) finds no optimum either
+    for b in np.nonzero(early)[0][::max(1, int(early.sum()) // 24)]:
+        K = int(on.K[b])
+        assert H.highs_solution("cub", batch, int(b), GOLDEN_W_CUB, ref0["segs"][b, :K]) is None, b
+    decided_solved = H.decided_classes(ref, ref0) & (ref0["status"] <= 1)
+    assert not (early & decided_solved).any()
+    assert np.all(on.a_cost[early] == api.FAIL_COST)
+    rest = ~early
+    assert np.array_equal(on.status[rest], off.status[rest]) and np.array_equal(on.iters[rest], off.iters[rest])
+    assert np.array_equal(on.ctrl[rest], off.ctrl[rest]) and np.array_equal(on.a_cost[rest], off.a_cost[rest])
+    assert on.segs.tobytes() == off.segs.tobytes() and np.array_equal(on.K, off.K)
+
+
 def test_async_pipeline_matches_sync(planner):
     """spectral_solve_batch_async / spectral_wait over page-locked buffers, three handles cycled like a sweep driver:
     bit-identical to the synchronous entry point."""

@@ -96,3 +96,16 @@ def test_emu_failure_classes():
     assert got.status[0] == api.FAIL_NO_CORRIDOR and got.K[0] == 0 and got.a_cost[0] == api.FAIL_COST
     got = H.emu_solve("trp", H.fixture_batch("c1"), WEIGHTS_FILE, k_max=4, max_iter=25)
     assert got.status[0] == api.FAIL_TOO_MANY and got.K[0] == 8
+
+
+def test_emu_infeasibility_precheck():
+    """The optional interval pre-check (SpectralOptions.infeasibility_precheck) fails provably empty corridors before
+    the first ADMM iteration and leaves the others alone (scenarios 914 and 5 of config 2 have disjoint joint intervals)."""
+    from spectral_b200.scenarios import GOLDEN_W_CUB
+    batch = _subset(config2(1024), [0, 914, 3, 5])
+    off = H.emu_solve("cub", batch, GOLDEN_W_CUB, max_iter=100)
+    on = H.emu_solve("cub", batch, GOLDEN_W_CUB, max_iter=100, infeasibility_precheck=1)
+    assert list(off.iters) == [100, 100, 100, 100]
+    assert list(on.iters) == [100, 0, 100, 0]
+    assert on.status[1] == on.status[3] == api.FAIL_SOLVER and on.a_cost[1] == api.FAIL_COST
+    assert np.array_equal(on.ctrl[[0, 2]], off.ctrl[[0, 2]])

@@ -76,6 +76,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
   od.adapt_every = opt->adaptive_rho_interval; od.polish = opt->polish; od.polish_refine = opt->polish_refine_iter;
   od.eps_abs = opt->eps_abs; od.eps_rel = opt->eps_rel; od.eps_pinf = opt->eps_prim_inf; od.rho0 = opt->rho;
   od.sigma = opt->sigma; od.alpha = opt->alpha; od.adapt_tol = opt->adaptive_rho_tolerance; od.polish_delta = opt->polish_delta; od.polish_rounds = opt->polish_rounds;
+  od.precheck = opt->infeasibility_precheck; od.precheck_margin = opt->precheck_margin;
   for (int cls = 0; cls < SP_NUM_CLASSES; cls++) {
     int cnt = (int)list[cls].size();
     if (!cnt) continue;
@@ -130,4 +131,5 @@ extern "C" void emu_default_options(SpectralOptions *o) {
   o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
   o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
   o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
+  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3;
 }

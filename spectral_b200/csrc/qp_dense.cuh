@@ -111,6 +111,9 @@ SP_DEV void qpd_lds2(const double *p, double &a, double &b) {
 #ifndef QPD_STAGE
 #define QPD_STAGE(KC) ((KC) <= 8)      // S3: the whole g chunk in flight (CH doubles of temporaries)
 #endif
+#ifndef QPD_STAGE_GROUP
+#define QPD_STAGE_GROUP(KC) 0  // S3 in groups of this many doubles where the whole chunk does not fit (0: unstaged; KC = 10 in groups of 10: 9.65 -> 10.2 ms)
+#endif
 #ifndef QPD_STAGE_ROWS
 #define QPD_STAGE_ROWS(KC) ((KC) <= 8)   // S2 / S1: 13 - 18 doubles of temporaries (KC = 10 at 128 registers: 9.5 -> 10.6 ms)
 #endif
@@ -528,16 +531,25 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
     {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       static_assert(CH % 2 == 0, "g chunks are loaded in 16-byte pairs");
-      double gl[CH];
+      // the g chunk in groups of GRP doubles: a run of loads, a scheduling fence, the FMAs (ptxas otherwise consumes each
+      // load before issuing the next); GRP = the whole chunk where the register budget allows
+      constexpr int GRP = QPD_STAGE(KC) ? CH : (QPD_STAGE_GROUP(KC) > 0 ? QPD_STAGE_GROUP(KC) : CH);
+      static_assert(GRP % 2 == 0, "groups of 16-byte pairs");
 #pragma unroll
-      for (int e = 0; e < CH; e += 2) qpd_lds2(gvh + e, gl[e], gl[e + 1]);
-      qpd_sched_fence_if<QPD_STAGE(KC)>();  // keeps the loads above in one back-to-back run (ptxas otherwise consumes each one before the next)
+      for (int g0 = 0; g0 < CH; g0 += GRP) {
+        double gl[GRP];
 #pragma unroll
-      for (int e = 0; e + 3 < CH; e += 4) {
-        a0 += G[e] * gl[e]; a1 += G[e + 1] * gl[e + 1]; a2 += G[e + 2] * gl[e + 2]; a3 += G[e + 3] * gl[e + 3];
+        for (int e = 0; e < GRP; e += 2)
+          if (g0 + e < CH) qpd_lds2(gvh + g0 + e, gl[e], gl[e + 1]);
+        qpd_sched_fence_if<QPD_STAGE(KC) || (QPD_STAGE_GROUP(KC) > 0)>();
+#pragma unroll
+        for (int e = 0; e < GRP; e += 2) {
+          if (g0 + e < CH) {
+            if ((e >> 1) & 1) { a2 += G[g0 + e] * gl[e]; a3 += G[g0 + e + 1] * gl[e + 1]; }
+            else { a0 += G[g0 + e] * gl[e]; a1 += G[g0 + e + 1] * gl[e + 1]; }
+          }
+        }
       }
-#pragma unroll
-      for (int e = CH & ~3; e < CH; e++) a0 += G[e] * gl[e];
       double xt = (a0 + a1) + (a2 + a3);
       xt += sp_shfl_xor(xt, 1);
       if (L::NCH == 4) xt += sp_shfl_xor(xt, 2);

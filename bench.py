@@ -370,7 +370,10 @@ def run_ours(args):
                          "note": "timed on one stream (pass A, %d steps) with CUDA events around the QP stage; the headline value overlaps %d steps" % (na, NS)},
             "roofline_corridor": {"kernel": "k_corridor", "bound": "hbm", "achieved": cor_gbs, "peak": peaks.get("hbm_gbs"),
                                   "unit": "GB/s", "frac": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                                  "traffic": None, "peak_source": peak_src, "ms_per_launch": cor_ms},
+                                  # ncu --set full at B = 65 536 (profiles/r1_small_kernels.md): 425 MB DRAM traffic per
+                                  # launch against 431 MB algorithmic, i.e. 6.49 KB per scenario -> per 1024-scenario launch
+                                  "traffic": 6.49e3 * B, "peak_source": peak_src, "ms_per_launch": cor_ms,
+                                  "note": "bound by the lane-0 replay of the sequential selection logic, not by HBM: 0.065 of peak even at B = 65 536 (1.0 ms)"},
             "kernel_ms_per_step": {k: kt[k] / calls for k in ("tables", "corridor", "classify", "qp", "finalize")},
             "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": _host_threads(), "kind": kind,
                              "sample": "first %d scenarios of one 1024-scenario batch, reference OSQP settings" % cpu_sample},

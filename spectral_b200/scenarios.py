@@ -61,6 +61,14 @@ def perturbed_obstacles(base: Scenario, B: int, seed: int = 20230531, first: int
     dl_hi = np.round(u[..., 3] * 0.6 - 0.3, 2)
     if first == 0:
         dk[0], ds[0], dl_lo[0], dl_hi[0] = 0, 0.0, 0.0, 0.0
+    return _shift_obstacles(base, dk, ds, dl_lo, dl_hi, s_max)
+
+
+def _shift_obstacles(base: Scenario, dk, ds, dl_lo, dl_hi, s_max: float = 50.0) -> ScenarioBatch:
+    """B copies of `base` whose obstacle ramps (the s-bound entries that differ from the region's free-road value) are
+    moved by dk[B, R] knots and ds[B, R] metres and whose lane edges are moved by dl_lo / dl_hi[B, R] metres."""
+    N, R = base.n_knots, base.n_regions
+    B = dk.shape[0]
     idx = np.arange(N)[None, None, :] - dk[..., None]          # source knot of each destination knot
     valid = (idx >= 0) & (idx < N)
     src = np.clip(idx, 0, N - 1)
@@ -82,6 +90,42 @@ def perturbed_obstacles(base: Scenario, B: int, seed: int = 20230531, first: int
     return ScenarioBatch(N, R, base.delta_t, np.ascontiguousarray(s_out), np.ascontiguousarray(l_out),
                          rep(base.ds_bounds), rep(base.dl_bounds), rep(base.s_ref), rep(base.l_ref),
                          rep(np.concatenate([base.init_s, base.init_l])), rep(base.scalars))
+
+
+def config3(B: int = 65536, groups: int = 8, first: int = 0, seed: int = 20230601) -> ScenarioBatch:
+    """BASELINE.json configs[2] (SURVEY.md 8d "Config 3"): scenario_2 (c2.txt, trapezoid-prism, N = 71, R = 1), variants
+    that leave the KKT STRUCTURE (segment count, time allocation, weights) of their group unchanged -- only bounds,
+    initial state and references differ -- in `groups` groups of distinct time allocations (scenario b belongs to group
+    b % groups; the group moves the obstacle ramp by a fixed number of knots, which moves the corridor breaks).
+    Within a group: the obstacle's s-bias is offset by round(U(-1,1), 2) m (slopes and breaks untouched), the ds / dl
+    bound columns by round(U(-0.5,0.5), 2), the initial (ds, dl) by U(-0.5,0.5) and the reference lines by a constant
+    round(U(-0.5,0.5), 2) m.  Scenario 0 is the unperturbed base."""
+    base = load_fixture("c2")
+    N, R = base.n_knots, base.n_regions
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    if first:
+        rng.bit_generator.advance(first * 2)  # two Philox blocks (8 draws) per scenario
+    u = rng.random((B, 8))
+    ids = first + np.arange(B)
+    shifts = np.array([0] + [d for k in range(1, 33) for d in (k, -k)])[:max(1, groups)]
+    dk = np.repeat(shifts[ids % max(1, groups)][:, None], R, axis=1)
+    ds = np.repeat(np.round(u[:, 0] * 2.0 - 1.0, 2)[:, None], R, axis=1)
+    zero = np.zeros((B, R))
+    unperturbed = ids == 0
+    ds[unperturbed] = 0.0
+    b = _shift_obstacles(base, dk, ds, zero, zero, 50.0)
+    off = lambda c: np.where(unperturbed, 0.0, np.round(u[:, c] - 0.5, 2))  # noqa: E731
+    ds_b = b.ds_bounds.copy()
+    ds_b[:, :, 1] = ds_b[:, :, 1] + off(1)[:, None]
+    dl_b = b.dl_bounds.copy()
+    dl_b[:, :, 1] = dl_b[:, :, 1] + off(2)[:, None]
+    init = b.init.copy()
+    init[:, 1] = np.maximum(init[:, 1] + np.where(unperturbed, 0.0, u[:, 3] - 0.5), 0.0)
+    init[:, 4] = init[:, 4] + np.where(unperturbed, 0.0, 0.2 * (u[:, 4] - 0.5))
+    s_ref = b.s_ref.copy()
+    s_ref[:, 1:] = s_ref[:, 1:] + off(5)[:, None]   # knot 0 stays at the initial position
+    l_ref = b.l_ref + 0.2 * off(6)[:, None]
+    return ScenarioBatch(N, R, base.delta_t, b.s_bounds, b.l_bounds, ds_b, dl_b, s_ref, l_ref, init, b.scalars)
 
 
 def config2(B: int = 1024, first: int = 0) -> ScenarioBatch:

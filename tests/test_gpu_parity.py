@@ -12,7 +12,7 @@ import pytest
 import helpers as H
 import pyoracle as po
 from spectral_b200 import api
-from spectral_b200.scenarios import (GOLDEN_W_CUB, GOLDEN_W_TRP, WEIGHTS_FILE, config2, load_fixture, mixed_batches,
+from spectral_b200.scenarios import (GOLDEN_W_CUB, GOLDEN_W_TRP, WEIGHTS_FILE, config2, config3, load_fixture, mixed_batches,
                                      perturbed_obstacles)
 from spectral_b200.wire import ScenarioBatch, read_trajectory_text, write_scenario_text
 
@@ -133,6 +133,17 @@ def test_config2_trp_512_vs_oracle(planner):
     got = planner.solve("trp", batch, GOLDEN_W_TRP)
     ref, ref0 = H.oracle_pair("trp", batch, GOLDEN_W_TRP)
     H.assert_batch_parity(got, ref, "trp512", need_verified_frac=0.6, ref0=ref0, batch=batch, variant="trp", weights=GOLDEN_W_TRP)
+
+
+def test_config3_shared_structure_groups_vs_oracle(planner):
+    """BASELINE configs[2] at test size: scenario_2 (c2.txt), trapezoid-prism, 8 groups sharing one KKT structure each."""
+    batch = config3(512, groups=8)
+    got = planner.solve("trp", batch, WEIGHTS_FILE)
+    ref, ref0 = H.oracle_pair("trp", batch, WEIGHTS_FILE)
+    H.assert_batch_parity(got, ref, "config3", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="trp", weights=WEIGHTS_FILE)
+    for g in range(8):  # one structure per group, as the generator promises
+        m = np.arange(512) % 8 == g
+        assert len(set(got.K[m])) == 1
 
 
 def test_mixed_variable_structure_vs_oracle(planner):

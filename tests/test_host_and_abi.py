@@ -156,3 +156,22 @@ def test_reference_wrapper_surface_is_mirrored():
         finally:
             os.environ.pop("SPECTRAL_IO_DIR", None)
         assert [a[0] for a in tr.asked] == names[:10] and all(a[1:] == (0, 50) for a in tr.asked)
+
+
+def test_config3_groups_share_one_kkt_structure():
+    """BASELINE configs[2] generator: within a group every scenario has the same segment count and time allocation (the
+    KKT structure), only bounds / initial state / references differ; groups differ in their time allocation; scenario b
+    does not depend on the batch it is generated in."""
+    import pyoracle as po
+    from spectral_b200.scenarios import WEIGHTS_FILE, config3
+    G, B = 8, 256
+    batch = config3(B, groups=G)
+    r = po.solve_batch("trp", batch, WEIGHTS_FILE, mode=0, nthreads=0)
+    sig = [(int(r["K"][b]),) + tuple(np.round(r["segs"][b, :r["K"][b]]["t"], 9)) for b in range(B)]
+    per_group = [set(sig[b] for b in range(B) if b % G == g) for g in range(G)]
+    assert all(len(x) == 1 for x in per_group), per_group
+    assert len(set.union(*per_group)) >= G - 1
+    assert not np.array_equal(batch.s_bounds[G], batch.s_bounds[2 * G])  # same group, different bounds
+    tail = config3(16, groups=G, first=B - 16)
+    for a, b in zip(tail.arrays(), batch.arrays()):
+        assert np.array_equal(a, b[B - 16:])

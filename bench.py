@@ -375,6 +375,15 @@ def run_ours(args):
                                   "traffic": 6.49e3 * B, "peak_source": peak_src, "ms_per_launch": cor_ms,
                                   "note": "bound by the lane-0 replay of the sequential selection logic, not by HBM: 0.065 of peak even at B = 65 536 (1.0 ms)"},
             "kernel_ms_per_step": {k: kt[k] / calls for k in ("tables", "corridor", "classify", "qp", "finalize")},
+            # every kernel of the step with the resource that bounds it (ncu evidence: profiles/r1_qpd_full.md,
+            # profiles/r1_small_kernels.md); shares from the CUDA-event ring of pass A
+            "kernels": [
+                {"kernel": "k_qpd<8|10|12|16> (ADMM)", "bound": "fp64 / shared-memory pipe / latency", "share": kt["qp"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9),
+                 "frac_of_fp64_peak": achieved_tf / fp64_peak if fp64_peak else None},
+                {"kernel": "k_corridor", "bound": "hbm", "share": kt["corridor"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9),
+                 "frac_of_hbm_peak": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
+                {"kernel": "k_finalize", "bound": "latency (8 CTAs)", "share": kt["finalize"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9)},
+                {"kernel": "k_tables + k_classify", "bound": "launch latency (one CTA each)", "share": (kt["tables"] + kt["classify"]) / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9)}],
             "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": _host_threads(), "kind": kind,
                              "sample": "first %d scenarios of one 1024-scenario batch, reference OSQP settings" % cpu_sample},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h)},

@@ -48,14 +48,25 @@
 // common K <= 8 class -- with 4, the warps run the variable gather with a quarter of their lanes and the total
 // instruction / shared-memory wavefront count per iteration rises 59 % / 69 %.  4 chunks (a quarter row of G and at
 // most one constraint row per thread) are kept where 2 would not fit the register file (KC >= 12).
+// V-major layout (QPD_VMAJOR): 4 chunks per row of G with the chunk index h UNIFORM PER WARP (thread t = h N + v), so
+// that the broadcast load of the g chunk costs one shared-memory wavefront per LDS.128 instead of one per distinct
+// address (with the chunk lanes adjacent: 4); the four partial sums of a variable meet in shared memory (one more
+// barrier), the gather and the partial-sum reduction run on the h = 0 warps only, every thread owns one constraint row.
+// Measured on B200 for K <= 8 (profiles/r1_qpd_staging.md): 14.6 ms against 11.6 ms of the row-pair layout -- 29 % more
+// instructions, a fourth barrier over 12 warps and no room for staged loads at 80 registers outweigh the cheaper
+// broadcast.  Kept behind the switch (off) as the measured alternative.
+#ifndef QPD_VMAJOR
+#define QPD_VMAJOR(KC) 0
+#endif
 #ifndef QPD_NCH
-#define QPD_NCH(KC) ((KC) >= 12 ? 4 : 2)
+#define QPD_NCH(KC) (((KC) >= 12 || QPD_VMAJOR(KC)) ? 4 : 2)
 #endif
 SP_HD constexpr int qpd_nch(int KC) { return QPD_NCH(KC); }
 
 template <int KC>
 struct QpdLayout {
   static constexpr int NCH = qpd_nch(KC);      // threads per variable (chunks per row of G)
+  static constexpr bool VMAJOR = QPD_VMAJOR(KC); // thread t = h N + v (chunk index uniform per warp) instead of t = v NCH + h
   static_assert(KC % NCH == 0, "the chunks of a row of G split the segments evenly");
   static constexpr int N = 6 * KC;             // variables per axis
   static constexpr int CH = N / NCH;           // columns of G per thread
@@ -85,7 +96,8 @@ struct QpdLayout {
   static constexpr int O_CE = O_XR + N + 8;                          // continuity row coefficients [3KC][6]
   static constexpr int O_VCF = O_CE + 18 * KC;                       // continuity gather coefficients [N][3]
   static constexpr int O_LU = ((O_VCF + 3 * N + 1) / 2) * 2;         // (l, u) of the row slots [3][TA] pairs (16-byte aligned)
-  static constexpr int AXIS = O_LU + 6 * TA;                         // doubles per axis (even)
+  static constexpr int O_PS = O_LU + 6 * TA;                         // v-major layout: partial sums of x~ [NCH][N]
+  static constexpr int AXIS = O_PS + (VMAJOR ? ((NCH * N + 1) / 2) * 2 : 0);  // doubles per axis (even)
   // per-CTA tail: reduction scratch [NWARPS][QPD_NRED], eqmask ints [2][LPA]
   static constexpr int O_RED = 2 * AXIS;
   static constexpr int O_EQ = O_RED + NWARPS * QPD_NRED;
@@ -225,6 +237,55 @@ SP_DEV void qpd_inverse_chunk(const double *fs, int v, int h, double *g) {
     if (phase > 0) {  // lane h - 1 takes over with lane h's x
       const double t0 = sp_shfl_down(n0, 1, NCH), t1 = sp_shfl_down(n1, 1, NCH), t2 = sp_shfl_down(n2, 1, NCH);
       if (h == phase - 1) { n0 = t0; n1 = t1; n2 = t2; }
+    }
+  }
+}
+
+// thread -> (variable v, chunk h) of the G layout; threads beyond NCH N hold nothing (v = N)
+template <int KC>
+SP_DEV void qpd_map(int ta, int &v, int &h) {
+  using L = QpdLayout<KC>;
+  if (L::VMAJOR) { h = ta / L::N; v = ta - h * L::N; if (h >= L::NCH) { h = 0; v = L::N; } }
+  else { v = ta / L::NCH; h = ta % L::NCH; }
+}
+
+// V-major layout: chunk h of row v of G = S^-1 by ONE thread (the chunk lanes are not adjacent, so there is no carry to
+// hand over): the whole block forward / backward substitution on e_v with the intermediate vector in local memory,
+// keeping the KC / NCH segments of the chunk.  Runs at setup and after adaptive-rho updates only.
+template <int KC>
+SP_DEV void qpd_inverse_row_chunk(const double *fs, int v, int h, double *g) {
+  constexpr int KB = QpdLayout<KC>::KB, N = QpdLayout<KC>::N;
+  const int kv = v / 6, iv = v - 6 * kv;
+  const int kbase = h * KB;
+  double Y[N];
+  double c3 = 0.0, c4 = 0.0, c5 = 0.0;  // y_{k-1}[3..5]
+  for (int k = 0; k < KC; k++) {
+    const double *F = fs + 57 * k;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      double y = 0.0;
+      if (k == kv && a >= iv) y = F[LT(a, 0) + iv];
+      y -= F[21 + a * 3 + 0] * c3 + F[21 + a * 3 + 1] * c4 + F[21 + a * 3 + 2] * c5;  // C_0 = 0
+      Y[6 * k + a] = y;
+    }
+    c3 = Y[6 * k + 3]; c4 = Y[6 * k + 4]; c5 = Y[6 * k + 5];
+  }
+  double n0 = 0.0, n1 = 0.0, n2 = 0.0;  // x_{k+1}[0..2]
+  for (int k = KC - 1; k >= kbase; k--) {
+    const double *F = fs + 57 * k;
+    double x[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      double xx = 0.0;
+#pragma unroll
+      for (int a = i; a < 6; a++) xx += F[LT(a, i)] * Y[6 * k + a];
+      xx -= F[39 + i * 3 + 0] * n0 + F[39 + i * 3 + 1] * n1 + F[39 + i * 3 + 2] * n2;  // E of the last segment = 0
+      x[i] = xx;
+    }
+    n0 = x[0]; n1 = x[1]; n2 = x[2];
+    if (k < kbase + KB) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) g[6 * (k - kbase) + i] = x[i];
     }
   }
 }
@@ -388,7 +449,13 @@ SP_DEV void qpd_decode_diff(int e, int &order, int &k, int &i) {
 template <int KC>
 SP_DEV_NOINLINE void qpd_build_g(const double *fs, int v, int h, bool isg, double *out) {
   double g[QpdLayout<KC>::CH];
-  qpd_inverse_chunk<KC>(fs, v, h, g);
+  if constexpr (QpdLayout<KC>::VMAJOR) {
+#pragma unroll
+    for (int e = 0; e < QpdLayout<KC>::CH; e++) g[e] = 0.0;
+    if (isg) qpd_inverse_row_chunk<KC>(fs, v, h, g);
+  } else {
+    qpd_inverse_chunk<KC>(fs, v, h, g);
+  }
 #pragma unroll
   for (int e = 0; e < QpdLayout<KC>::CH; e++) out[e] = isg ? g[e] : 0.0;
 }
@@ -682,6 +749,76 @@ SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
   io.xv = xv;
 }
 
+// The v-major form of the block (QPD_VMAJOR): thread t = h N + v.  Four barriers per iteration:
+//   S2  (h = 0 warps) g_v = (A' V)_v + sigma x - q        the whole 13-load gather per variable thread
+//   S3  (all)         partial_h[v] = G[v][chunk h] . g[chunk h]   g chunk by warp-uniform LDS.128 (one wavefront each)
+//   S3b (h = 0 warps) x~_v = sum_h partial_h[v], x = alpha x~ + (1 - alpha) x
+//   S1  (all)         one constraint row per thread: z~ = (A x~)_row, w += alpha (z~ - clip(w)), next v -> V
+template <int KC, typename SyncFn>
+SP_DEV_NOINLINE void qpd_block5(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+  using L = QpdLayout<KC>;
+  constexpr int N = L::N, CH = L::CH, TA = L::TA;
+  static_assert(L::VMAJOR && L::NCH == 4 && !L::TWO_SLOTS && CH % 4 == 0, "v-major layout");
+  int v, h;
+  qpd_map<KC>(ta, v, h);
+  const bool isg = v < N;
+  const bool isvar = isg && h == 0;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
+  const double *vb = smx + L::O_V + QPD_VB * vk;
+  const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
+  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);  // continuity gather coefficients (zero for unused segments)
+  double *gvp = smx + L::O_GV + (isg ? v : 0);
+  const double *gvh = smx + L::O_GV + CH * h;
+  double *psp = smx + L::O_PS + h * N + (isg ? v : 0);
+  const double *ps0 = smx + L::O_PS + (isg ? v : 0);
+  double *cxp = smx + L::O_C + QPD_CP + (isg ? v : 0);
+  // the thread's row
+  const bool isj = io.rows[2].meta & 8;
+  const int ri = isj ? 2 : 0;
+  QpdRow r = io.rows[ri];
+  const bool rvalid = r.meta & 8;
+  const int order = r.meta & 3;
+  const double *cp = smx + L::O_C + r.coff;
+  double *vp = smx + L::O_V + r.voff;
+  const QpdLU *lu = (const QpdLU *)(smx + L::O_LU) + ta + (isj ? 2 * TA : 0);
+  const double *cej = smx + L::O_CE + 6 * (isj ? 3 * ((r.meta >> 8) & 0xff) + ((r.meta >> 16) - 18) : 0);
+  double xv = io.xv;
+  const double sigv = io.sigv, qv = io.qv, tkv = io.tkv;
+  double G[CH];
+#pragma unroll
+  for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  double yo = 0.0;
+  for (int i = 0; i < n; i++) {
+    if (i == n - 1) yo = r.rho * (r.w - r.p);
+    if (isvar) *gvp = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]) + sigv * xv - qv;  // S2
+    sync_cta();
+    {  // S3
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int e = 0; e < CH; e += 4) {
+        a0 += G[e] * gvh[e]; a1 += G[e + 1] * gvh[e + 1]; a2 += G[e + 2] * gvh[e + 2]; a3 += G[e + 3] * gvh[e + 3];
+      }
+      if (isg) *psp = (a0 + a1) + (a2 + a3);
+    }
+    sync_cta();
+    if (isvar) {  // S3b
+      const double xt = (ps0[0] + ps0[N]) + (ps0[2 * N] + ps0[3 * N]);
+      xv = alpha * xt + (1.0 - alpha) * xv;
+      *cxp = xt;
+    }
+    sync_cta();
+    if (rvalid) {  // S1
+      const QpdLU b = lu[0];
+      const double zt = isj ? qpd_join_row(cp, cej) : qpd_diff_row(cp, order, r.scale);
+      *vp = qpd_row_update(r, b, zt, alpha);
+    }
+    sync_cta();
+  }
+  io.rows[ri].w = r.w; io.rows[ri].p = r.p;
+  io.yo[0] = 0.0; io.yo[1] = 0.0; io.yo[2] = 0.0; io.yo[ri] = yo;
+  io.xv = xv;
+}
+
 // OSQP's termination test (residuals in the scaled space, scaled_termination = 1), primal-infeasibility
 // certificate and adaptive-rho rule, evaluated CTA-wide = jointly over the s and l problems of the scenario.
 // Called by all threads of the CTA on check iterations.
@@ -700,7 +837,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   const double *lsx = smx + L::O_LS;
   const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
   const double *cej = smx + L::O_CE + 6 * ((io.rows[2].meta & 8) ? 3 * ((io.rows[2].meta >> 8) & 0xff) + ((io.rows[2].meta >> 16) - 18) : 0);
-  const int v = ta / L::NCH, h = ta % L::NCH;
+  int v, h;
+  qpd_map<KC>(ta, v, h);
   const bool isg = v < N;
   const bool isvar = isg && h == 0;
   const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
@@ -849,7 +987,8 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     rj.er = sqrt(rj.rho * (c_scale / rhobar) * (eq ? 1e-3 : 1.0));
   }
   // G thread (v, h); the h = 0 thread is the variable thread of v
-  const int v = ta / L::NCH, h = ta % L::NCH;
+  int v, h;
+  qpd_map<KC>(ta, v, h);
   const bool isg = v < N;
   const bool isvar = isg && h == 0;
   const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
@@ -881,7 +1020,8 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
     // one out-of-line call per check interval; before its LAST iteration the block captures the multipliers
     // y = rho (w - clip(w)) of the thread's rows (io.yo) for the delta y of the check
-    if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
+    if constexpr (L::VMAJOR) qpd_block5<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
+    else if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     else qpd_block<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     iters = it_end;
     it = it_end + 1;

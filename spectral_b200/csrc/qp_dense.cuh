@@ -58,8 +58,16 @@
 #ifndef QPD_VMAJOR
 #define QPD_VMAJOR(KC) 0
 #endif
+// Full-row layout (QPD_ROWFULL): ONE thread per variable holds its whole row of G (n doubles) -- 64 threads per axis,
+// 128 per CTA, up to 255 registers, still two CTAs per SM.  No chunk reduction (no shuffles), the g vector is read with
+// every lane on the same address (one wavefront per LDS.128), the gather runs on all variable lanes, and every thread
+// carries ceil(21 KC / 64) constraint rows whose loads and updates interleave (ILP instead of TLP: the kernel is
+// latency-bound and every wider layout tried lost to its extra barriers and instructions, profiles/r1_qpd_staging.md).
+#ifndef QPD_ROWFULL
+#define QPD_ROWFULL(KC) ((KC) == 10)
+#endif
 #ifndef QPD_NCH
-#define QPD_NCH(KC) (((KC) >= 12 || QPD_VMAJOR(KC)) ? 4 : 2)
+#define QPD_NCH(KC) (QPD_ROWFULL(KC) ? 1 : (((KC) >= 12 || QPD_VMAJOR(KC)) ? 4 : 2))
 #endif
 SP_HD constexpr int qpd_nch(int KC) { return QPD_NCH(KC); }
 
@@ -67,6 +75,7 @@ template <int KC>
 struct QpdLayout {
   static constexpr int NCH = qpd_nch(KC);      // threads per variable (chunks per row of G)
   static constexpr bool VMAJOR = QPD_VMAJOR(KC); // thread t = h N + v (chunk index uniform per warp) instead of t = v NCH + h
+  static constexpr bool ROWFULL = QPD_ROWFULL(KC); // thread t = variable t, whole row of G, NSLOT generic row slots
   static_assert(KC % NCH == 0, "the chunks of a row of G split the segments evenly");
   static constexpr int N = 6 * KC;             // variables per axis
   static constexpr int CH = N / NCH;           // columns of G per thread
@@ -82,7 +91,10 @@ struct QpdLayout {
   static constexpr bool TWO_SLOTS = NCH == 2;
   static constexpr int T0 = TWO_SLOTS ? ((NJ + 31) / 32) * 32 : 0;
   static constexpr int TN = TA - T0;
-  static_assert(TWO_SLOTS ? (2 * TN + T0 >= NN) : (TA >= ROWS), "row slots");
+  // row slots per thread.  Legacy layouts: 3 (difference rows A, B and one continuity row J).  Full-row layout: slot s of
+  // thread t holds row s TA + t of the unified numbering [0, NN) difference rows, [NN, ROWS) continuity / init rows.
+  static constexpr int NSLOT = ROWFULL ? (ROWS + TA - 1) / TA : 3;
+  static_assert(ROWFULL ? (NSLOT * TA >= ROWS) : (TWO_SLOTS ? (2 * TN + T0 >= NN) : (TA >= ROWS)), "row slots");
   static constexpr int LPA = KC <= 8 ? 8 : 16; // lanes per axis of the lane-per-segment (control) code
   static constexpr int STR = LPA;              // its shared-memory stride
   // per-axis shared memory (doubles)
@@ -95,8 +107,8 @@ struct QpdLayout {
   static constexpr int O_XR = O_C + N + 8;                           // relaxed x for the checks, same shape
   static constexpr int O_CE = O_XR + N + 8;                          // continuity row coefficients [3KC][6]
   static constexpr int O_VCF = O_CE + 18 * KC;                       // continuity gather coefficients [N][3]
-  static constexpr int O_LU = ((O_VCF + 3 * N + 1) / 2) * 2;         // (l, u) of the row slots [3][TA] pairs (16-byte aligned)
-  static constexpr int O_PS = O_LU + 6 * TA;                         // v-major layout: partial sums of x~ [NCH][N]
+  static constexpr int O_LU = ((O_VCF + 3 * N + 1) / 2) * 2;         // (l, u) of the row slots [NSLOT][TA] pairs (16-byte aligned)
+  static constexpr int O_PS = O_LU + 2 * NSLOT * TA;                 // v-major layout: partial sums of x~ [NCH][N]
   static constexpr int AXIS = O_PS + (VMAJOR ? ((NCH * N + 1) / 2) * 2 : 0);  // doubles per axis (even)
   // per-CTA tail: reduction scratch [NWARPS][QPD_NRED], eqmask ints [2][LPA]
   static constexpr int O_RED = 2 * AXIS;
@@ -125,6 +137,9 @@ SP_DEV void qpd_lds2(const double *p, double &a, double &b) {
 #endif
 #ifndef QPD_STAGE_GROUP
 #define QPD_STAGE_GROUP(KC) 0  // S3 in groups of this many doubles where the whole chunk does not fit (0: unstaged; KC = 10 in groups of 10: 9.65 -> 10.2 ms)
+#endif
+#ifndef QPD_LU_REG
+#define QPD_LU_REG(KC) ((KC) <= 8)   // (l, u) of the row slots in registers instead of one LDS.128 per slot and iteration
 #endif
 #ifndef QPD_STAGE_ROWS
 #define QPD_STAGE_ROWS(KC) ((KC) <= 8)   // S2 / S1: 13 - 18 doubles of temporaries (KC = 10 at 128 registers: 9.5 -> 10.6 ms)
@@ -440,10 +455,16 @@ SP_DEV_NOINLINE void qpd_control_finish(const QpArgs &a, int slot, int lane, dou
 // decode a difference-row index e in [0, 18 KC): order (0 containment .. 3 jerk), segment k, index i
 template <int KC>
 SP_DEV void qpd_decode_diff(int e, int &order, int &k, int &i) {
-  if (e < 6 * KC) { order = 0; k = e / 6; i = e - 6 * k; }
-  else if (e < 11 * KC) { order = 1; k = (e - 6 * KC) / 5; i = (e - 6 * KC) - 5 * k; }
-  else if (e < 15 * KC) { order = 2; k = (e - 11 * KC) / 4; i = (e - 11 * KC) - 4 * k; }
-  else { order = 3; k = (e - 15 * KC) / 3; i = (e - 15 * KC) - 3 * k; }
+  // within an order the SEGMENT index runs fastest: consecutive lanes then read stencil windows 6 doubles apart and write
+  // V entries 38 doubles apart -- both = 6 mod 16, i.e. the 16 lanes of an 8-byte shared-memory wavefront hit 16 distinct
+  // bank pairs (with the index i fastest the windows jump at every segment boundary and the accesses took 4 wavefronts
+  // instead of 2: profiles/r1_qpd_hotloop.md)
+  int ep;
+  if (e < 6 * KC) { order = 0; ep = e; }
+  else if (e < 11 * KC) { order = 1; ep = e - 6 * KC; }
+  else if (e < 15 * KC) { order = 2; ep = e - 11 * KC; }
+  else { order = 3; ep = e - 15 * KC; }
+  i = ep / KC; k = ep - KC * i;
 }
 
 template <int KC>
@@ -482,6 +503,46 @@ SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl,
   lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
   r.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
   r.er = sqrt(r.rho * c_over_rhobar * (eq ? 1e-3 : 1.0));
+}
+
+// initial state of a continuity / initial-state row slot: ej = row index in [0, 3 KC) or < 0 (no row)
+template <int KC>
+SP_DEV void qpd_init_join(QpdRow &rj, QpdLU &lu, int ej, int K, const double *ctl, const int *eqa, double c_over_rhobar) {
+  using L = QpdLayout<KC>;
+  constexpr int STR = L::STR;
+  const bool jvalid = ej >= 0 && ej < L::NJ;
+  const int k = jvalid ? ej / 3 : 0, rr = jvalid ? ej - 3 * k : 0;
+  const int r_old = 18 + rr;
+  const bool live = jvalid && k < K;
+  const int ooff = r_old * STR + k;
+  const int eq = live ? ((eqa[k] >> r_old) & 1) : 0;
+  rj.coff = 6 * k;  // window [c_{k-1,3..5}, c_{k,0..2}] starts at QPD_CP + 6k - 3
+  rj.voff = QPD_VB * k + QPD_VC + rr;
+  rj.meta = (jvalid ? 8 : 0) | (eq ? 16 : 0) | (k << 8) | (r_old << 16);
+  rj.scale = 0.0;
+  rj.w = 0.0; rj.p = 0.0;
+  lu.l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
+  lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
+  rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
+  rj.er = sqrt(rj.rho * c_over_rhobar * (eq ? 1e-3 : 1.0));
+}
+// a row slot of the unified numbering: [0, NN) difference rows, [NN, ROWS) continuity / initial-state rows, else none
+template <int KC>
+SP_DEV void qpd_init_row(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl, const double *lsx, const int *eqa, double c_over_rhobar) {
+  using L = QpdLayout<KC>;
+  if (e >= L::NN && e < L::ROWS) qpd_init_join<KC>(r, lu, e - L::NN, K, ctl, eqa, c_over_rhobar);
+  else qpd_init_diff<KC>(r, lu, e < L::NN ? e : -1, K, ctl, lsx, eqa, c_over_rhobar);
+}
+SP_DEV bool qpd_row_is_join(const QpdRow &r) { return (r.meta >> 16) >= 18; }
+// (A x)_row for any row slot: xbase = the padded control-point array (C or XR) of the axis
+template <int KC>
+SP_DEV double qpd_row_eval(const QpdRow &r, const double *xbase, const double *smx) {
+  using L = QpdLayout<KC>;
+  if (qpd_row_is_join(r)) {
+    const double *cej = smx + L::O_CE + 6 * (3 * ((r.meta >> 8) & 0xff) + ((r.meta >> 16) - 18));
+    return qpd_join_row(xbase + r.coff, cej);
+  }
+  return qpd_diff_row(xbase + r.coff, r.meta & 3, r.scale);
 }
 
 // max as one compare-select (fmax expands to a NaN-propagation sequence four times as long); a NaN in b is dropped
@@ -531,11 +592,11 @@ SP_DEV double qpd_row_update(QpdRow &r, const QpdLU &b, double zt, double alpha)
 
 // The per-thread state of the dense loop.  It lives in local memory in the CTA body; qpd_block loads what it needs
 // into registers for a block of iterations, qpd_check / qpd_build_g work on it in place.
-template <int CHN>
+template <int CHN, int NS = 3>
 struct QpdIOT {
   double G[CHN];    // this thread's chunk of its row of G = S^-1
-  QpdRow rows[3];   // row slots: two difference rows (A, B) and one continuity row (J); unused ones have meta bit 3 clear
-  double yo[3];     // multipliers before the check iteration's update
+  QpdRow rows[NS];  // row slots (legacy layouts: difference rows A, B and continuity row J); unused ones have meta bit 3 clear
+  double yo[NS];    // multipliers before the check iteration's update
   double xv, sigv, qv, tkv;  // variable thread: relaxed iterate, sigma, q, segment duration
   double c_scale, rhobar;
   int state, need_g, it;
@@ -546,7 +607,7 @@ struct QpdIOT {
 //   S3  x~ = G g (one chunk of the row per thread, the partner lanes hold the others), x = alpha x~ + (1 - alpha) x
 //   S1  z~ = A x~ (stencils), w += alpha (z~ - clip(w)), next v -> V
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int N = L::N, CH = L::CH, TA = L::TA;
   const int v = ta / L::NCH, h = ta % L::NCH;
@@ -577,6 +638,9 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
   double G[CH];
 #pragma unroll
   for (int e = 0; e < CH; e++) G[e] = io.G[e];
+  // where the register budget allows, the (l, u) pairs of both slots stay in registers for the whole block
+  constexpr bool LU_REG = QPD_LU_REG(KC);
+  const QpdLU la_r = lua[0], l2_r = lu2[0];
   double yoa = 0.0, yo2 = 0.0;
   for (int i = 0; i < n; i++) {
     if (i == n - 1) { yoa = ra.rho * (ra.w - ra.p); yo2 = r2.rho * (r2.w - r2.p); }
@@ -632,7 +696,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
     if (second_is_b) {
       const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
       const double b0 = cp2[0], b1 = cp2[1], b2 = cp2[2], b3 = cp2[3];
-      const QpdLU la = lua[0], lb = lu2[0];
+      const QpdLU la = LU_REG ? la_r : lua[0], lb = LU_REG ? l2_r : lu2[0];
       qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       const double wa[4] = {a0, a1, a2, a3}, wb[4] = {b0, b1, b2, b3};
       const double za = qpd_diff_row(wa, oa, ra.scale), zb = qpd_diff_row(wb, ob, r2.scale);
@@ -643,7 +707,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
       const double a0 = cpa[0], a1 = cpa[1], a2 = cpa[2], a3 = cpa[3];
       const double j0 = cp2[0], j1 = cp2[1], j2 = cp2[2], j3 = cp2[3], j4 = cp2[4], j5 = cp2[5];
       const double e0 = cej[0], e1 = cej[1], e2 = cej[2], e3 = cej[3], e4 = cej[4], e5 = cej[5];
-      const QpdLU la = lua[0], lj = lu2[0];
+      const QpdLU la = LU_REG ? la_r : lua[0], lj = LU_REG ? l2_r : lu2[0];
       qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       const double wa[4] = {a0, a1, a2, a3};
       const double za = qpd_diff_row(wa, oa, ra.scale);
@@ -666,7 +730,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int t
 //   h = 0: t_k V0[j] + 5 (V1[j-1] - V1[j]) + sigma x - q      h = 1: 20 (V2[j-2] - 2 V2[j-1] + V2[j])
 //   h = 2: 60 (V3[j-3] - 3 V3[j-2] + 3 V3[j-1] - V3[j])        h = 3: the three continuity rows that touch the variable
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int N = L::N, CH = L::CH, TA = L::TA;
   static_assert(L::NCH == 4 && !L::TWO_SLOTS, "one row per thread");
@@ -755,7 +819,7 @@ SP_DEV_NOINLINE void qpd_block4(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
 //   S3b (h = 0 warps) x~_v = sum_h partial_h[v], x = alpha x~ + (1 - alpha) x
 //   S1  (all)         one constraint row per thread: z~ = (A x~)_row, w += alpha (z~ - clip(w)), next v -> V
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpd_block5(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
+SP_DEV_NOINLINE void qpd_block5(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &io, double *smx, int ta, int n, double alpha, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int N = L::N, CH = L::CH, TA = L::TA;
   static_assert(L::VMAJOR && L::NCH == 4 && !L::TWO_SLOTS && CH % 4 == 0, "v-major layout");
@@ -819,11 +883,121 @@ SP_DEV_NOINLINE void qpd_block5(QpdIOT<QpdLayout<KC>::CH> &io, double *smx, int 
   io.xv = xv;
 }
 
+// The full-row form of the block (QPD_ROWFULL): thread t < N is variable t and holds ROW t of G entirely; every thread
+// carries NSLOT constraint rows (slot s = row s TA + t of the unified numbering).  Three barriers per iteration:
+//   S2  g_t = (A' V)_t + sigma x - q          13 loads in one run, then the arithmetic
+//   S3  x~_t = G[t][:] . g                     g read by every lane from the same address (one wavefront per LDS.128),
+//                                               in groups of GRP doubles: loads, scheduling fence, FMAs
+//   S1  the thread's rows: z~ = (A x~)_row, w += alpha (z~ - clip(w)), next v -> V; all-difference slots as one
+//       straight-line stream, the slot(s) that mix difference and continuity rows behind a branch
+template <int KC, typename SyncFn>
+SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &io, double *smx, int ta, int n, double alpha,
+                                SyncFn sync_cta) {
+  using L = QpdLayout<KC>;
+  constexpr int N = L::N, TA = L::TA, NS = L::NSLOT, NN = L::NN;
+  static_assert(L::ROWFULL && L::NCH == 1 && N % 4 == 0, "full-row layout");
+  constexpr int GRP = 12;  // doubles of g in flight per group (6 LDS.128)
+  static_assert(N % GRP == 0, "g in whole groups");
+  constexpr int ND = NN / TA;  // slots 0 .. ND-1 hold difference rows on every thread
+  const int v = ta;
+  const bool isg = v < N;
+  const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
+  const double *vb = smx + L::O_V + QPD_VB * vk;
+  const double *vkk = smx + L::O_V + QPD_VB * (vj < 3 ? vk : vk + 1);
+  const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);  // continuity gather coefficients (zero for unused segments)
+  double *gvp = smx + L::O_GV + (isg ? v : 0);
+  const double *gv = smx + L::O_GV;
+  double *cx = smx + L::O_C;
+  double *cxp = cx + QPD_CP + (isg ? v : 0);
+  double *vv = smx + L::O_V;
+  const QpdLU *lu0 = (const QpdLU *)(smx + L::O_LU) + ta;
+  QpdRow r[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) r[sl] = io.rows[sl];
+  double xv = io.xv;
+  const double sigv = io.sigv, qv = io.qv, tkv = io.tkv;
+  double G[N];
+#pragma unroll
+  for (int e = 0; e < N; e++) G[e] = io.G[e];
+  double yo[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) yo[sl] = 0.0;
+  for (int i = 0; i < n; i++) {
+    if (i == n - 1) {
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) yo[sl] = r[sl].rho * (r[sl].w - r[sl].p);
+    }
+    if (isg) {  // S2
+      const double g0 = vb[QPD_V0 + vj], g1a = vb[QPD_V1 + vj - 1], g1b = vb[QPD_V1 + vj];
+      const double g2a = vb[QPD_V2 + vj - 2], g2b = vb[QPD_V2 + vj - 1], g2c = vb[QPD_V2 + vj];
+      const double g3a = vb[QPD_V3 + vj - 3], g3b = vb[QPD_V3 + vj - 2], g3c = vb[QPD_V3 + vj - 1], g3d = vb[QPD_V3 + vj];
+      const double c0 = vkk[QPD_VC], c1 = vkk[QPD_VC + 1], c2 = vkk[QPD_VC + 2];
+      const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];
+      qpd_sched_fence();
+      const double t01 = tkv * g0 + 5.0 * (g1a - g1b);
+      const double t2 = 20.0 * ((g2a - g2b) - (g2b - g2c));
+      const double t3 = 60.0 * ((g3a - g3d) + 3.0 * (g3c - g3b));
+      const double tc = (f0 * c0 + f1 * c1) + (f2 * c2 + (sigv * xv - qv));
+      *gvp = (t01 + t2) + (t3 + tc);
+    }
+    sync_cta();
+    {  // S3
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int g0 = 0; g0 < N; g0 += GRP) {
+        double gl[GRP];
+#pragma unroll
+        for (int e = 0; e < GRP; e += 2) qpd_lds2(gv + g0 + e, gl[e], gl[e + 1]);
+        qpd_sched_fence();
+#pragma unroll
+        for (int e = 0; e < GRP; e += 4) {
+          a0 += G[g0 + e] * gl[e]; a1 += G[g0 + e + 1] * gl[e + 1]; a2 += G[g0 + e + 2] * gl[e + 2]; a3 += G[g0 + e + 3] * gl[e + 3];
+        }
+      }
+      const double xt = (a0 + a1) + (a2 + a3);
+      if (isg) {
+        xv = alpha * xt + (1.0 - alpha) * xv;
+        *cxp = xt;
+      }
+    }
+    sync_cta();
+    {  // S1
+      double win[ND > 0 ? ND : 1][4];
+      QpdLU lub[NS];
+#pragma unroll
+      for (int sl = 0; sl < ND; sl++) {
+        const double *cp = cx + r[sl].coff;
+        win[sl][0] = cp[0]; win[sl][1] = cp[1]; win[sl][2] = cp[2]; win[sl][3] = cp[3];
+      }
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) lub[sl] = lu0[sl * TA];
+      qpd_sched_fence();
+#pragma unroll
+      for (int sl = 0; sl < ND; sl++) {
+        const double zt = qpd_diff_row(win[sl], r[sl].meta & 3, r[sl].scale);
+        const double u = qpd_row_update(r[sl], lub[sl], zt, alpha);
+        vv[r[sl].voff] = u;  // every thread has a row in these slots
+      }
+#pragma unroll
+      for (int sl = ND; sl < NS; sl++) {
+        if (r[sl].meta & 8) {
+          const double zt = qpd_row_eval<KC>(r[sl], cx, smx);
+          vv[r[sl].voff] = qpd_row_update(r[sl], lub[sl], zt, alpha);
+        }
+      }
+    }
+    sync_cta();
+  }
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) { io.rows[sl].w = r[sl].w; io.rows[sl].p = r[sl].p; io.yo[sl] = yo[sl]; }
+  io.xv = xv;
+}
+
 // OSQP's termination test (residuals in the scaled space, scaled_termination = 1), primal-infeasibility
 // certificate and adaptive-rho rule, evaluated CTA-wide = jointly over the s and l problems of the scenario.
 // Called by all threads of the CTA on check iterations.
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem, QpdIOT<QpdLayout<KC>::CH> &io, SyncFn sync_cta) {
+SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem, QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &io, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int N = L::N, LPA = L::LPA, STR = L::STR, TA = L::TA;
   (void)LPA;
@@ -835,8 +1009,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   const int K = a.K[a.list[slot]];
   const double *ctl = smx + L::O_CTRL;
   const double *lsx = smx + L::O_LS;
-  const QpdLU *lua = (const QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;
-  const double *cej = smx + L::O_CE + 6 * ((io.rows[2].meta & 8) ? 3 * ((io.rows[2].meta >> 8) & 0xff) + ((io.rows[2].meta >> 16) - 18) : 0);
+  constexpr int NS = L::NSLOT;
+  const QpdLU *lu0 = (const QpdLU *)(smx + L::O_LU) + ta;  // slot s: lu0[s * TA]
   int v, h;
   qpd_map<KC>(ta, v, h);
   const bool isg = v < N;
@@ -847,7 +1021,6 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   const double *vcf = smx + L::O_VCF + 3 * (isg ? v : 0);
   double *xr = smx + L::O_XR;
   double *vv = smx + L::O_V;
-  QpdRow &ra = io.rows[0], &rb = io.rows[1], &rj = io.rows[2];
   const double c_scale = io.c_scale, xv = io.xv, qv = io.qv, tkv = io.tkv;
   double rhobar = io.rhobar;
   int state = io.state;
@@ -858,9 +1031,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   for (int i = 0; i < QPD_NRED; i++) red_v[i] = 0.0;
   const double c_over_rhobar = c_scale / rhobar;
   // delta y of this iteration -> V (for A' delta y), its norm and the support-function term of the certificate
-  qpd_check_dy(ra, lua[0], io.yo[0], vv, c_scale, c_over_rhobar, red_v);
-  qpd_check_dy(rb, lub[0], io.yo[1], vv, c_scale, c_over_rhobar, red_v);
-  qpd_check_dy(rj, luj[0], io.yo[2], vv, c_scale, c_over_rhobar, red_v);
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) qpd_check_dy(io.rows[sl], lu0[sl * TA], io.yo[sl], vv, c_scale, c_over_rhobar, red_v);
   sync_cta();
   double cDv = 0.0;
   if (isvar) {
@@ -870,9 +1042,9 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
     xr[QPD_CP + v] = xv;
   }
   sync_cta();
-  if (ra.meta & 8) vv[ra.voff] = ra.rho * (ra.w - ra.p);  // y
-  if (rb.meta & 8) vv[rb.voff] = rb.rho * (rb.w - rb.p);
-  if (rj.meta & 8) vv[rj.voff] = rj.rho * (rj.w - rj.p);
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++)
+    if (io.rows[sl].meta & 8) vv[io.rows[sl].voff] = io.rows[sl].rho * (io.rows[sl].w - io.rows[sl].p);  // y
   sync_cta();
   if (isvar) {
     const double aty = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
@@ -889,9 +1061,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
     red_v[5] = cDv * fabs(px);
     red_v[6] = cDv * fabs(aty);
   }
-  qpd_check_resid(ra, qpd_diff_row(xr + ra.coff, ra.meta & 3, ra.scale), c_over_rhobar, red_v);
-  qpd_check_resid(rb, qpd_diff_row(xr + rb.coff, rb.meta & 3, rb.scale), c_over_rhobar, red_v);
-  qpd_check_resid(rj, qpd_join_row(xr + rj.coff, cej), c_over_rhobar, red_v);
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) qpd_check_resid(io.rows[sl], qpd_row_eval<KC>(io.rows[sl], xr, smx), c_over_rhobar, red_v);
   qpd_reduce(red_v, red, warp, lane, L::NWARPS, sync_cta);
   const double pri = red_v[0], dua = red_v[1], nz = red_v[2], nax = red_v[3], nq = red_v[4], npx = red_v[5], naty = red_v[6];
   const double nd = red_v[7], na = red_v[8], lhs = red_v[9];
@@ -908,9 +1079,8 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
     if (est > rhobar * o.adapt_tol || est < rhobar / o.adapt_tol) {
       const double ratio = est / rhobar;
       double *ctlw = smx + L::O_CTRL;
-      qpd_rescale_row(ra, ratio, K, ctlw + QP_SM_RHO * STR, STR);
-      qpd_rescale_row(rb, ratio, K, ctlw + QP_SM_RHO * STR, STR);
-      qpd_rescale_row(rj, ratio, K, ctlw + QP_SM_RHO * STR, STR);
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) qpd_rescale_row(io.rows[sl], ratio, K, ctlw + QP_SM_RHO * STR, STR);
       rhobar = est;
       sync_cta();
       if (warp == 0) qpd_control_refactor<KC>(a, slot, lane, smem, c_scale, rhobar);
@@ -955,9 +1125,13 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
   // ---------------- fast-layout state (lives in local memory; qpd_block keeps it in registers while it iterates) ----------------
   const double *ctl = smx + L::O_CTRL;
   const double *lsx = smx + L::O_LS;
-  QpdIOT<CH> io;
-  QpdLU *lua = (QpdLU *)(smx + L::O_LU) + ta, *lub = lua + TA, *luj = lub + TA;  // bounds of this thread's row slots
-  {
+  QpdIOT<CH, L::NSLOT> io;
+  QpdLU *lu0 = (QpdLU *)(smx + L::O_LU) + ta;  // bounds of this thread's row slots: lu0[s * TA]
+  if constexpr (L::ROWFULL) {
+#pragma unroll
+    for (int sl = 0; sl < L::NSLOT; sl++)
+      qpd_init_row<KC>(io.rows[sl], lu0[sl * TA], sl * TA + ta, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+  } else {
     int ea, eb, ej;
     if (L::TWO_SLOTS) {
       if (ta >= L::T0) { ea = ta - L::T0; eb = L::TN + (ta - L::T0); }
@@ -967,24 +1141,9 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       ea = ta < L::NN ? ta : -1; eb = -1;
       ej = (ta >= L::NN && ta < L::ROWS) ? ta - L::NN : -1;
     }
-    qpd_init_diff<KC>(io.rows[0], lua[0], ea, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
-    qpd_init_diff<KC>(io.rows[1], lub[0], eb, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
-    QpdRow &rj = io.rows[2];
-    const bool jvalid = ej >= 0;
-    const int k = jvalid ? ej / 3 : 0, rr = jvalid ? ej - 3 * k : 0;
-    const int r_old = 18 + rr;
-    const bool live = jvalid && k < K;
-    const int ooff = r_old * STR + k;
-    const int eq = live ? ((eqm[axis * LPA + k] >> r_old) & 1) : 0;
-    rj.coff = 6 * k;  // window [c_{k-1,3..5}, c_{k,0..2}] starts at QPD_CP + 6k - 3
-    rj.voff = QPD_VB * k + QPD_VC + rr;
-    rj.meta = (jvalid ? 8 : 0) | (eq ? 16 : 0) | (k << 8) | (r_old << 16);
-    rj.scale = 0.0;
-    rj.w = 0.0; rj.p = 0.0;
-    luj[0].l = live ? ctl[QP_SM_L * STR + ooff] : -1.0;
-    luj[0].u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
-    rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
-    rj.er = sqrt(rj.rho * (c_scale / rhobar) * (eq ? 1e-3 : 1.0));
+    qpd_init_diff<KC>(io.rows[0], lu0[0], ea, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+    qpd_init_diff<KC>(io.rows[1], lu0[TA], eb, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+    qpd_init_join<KC>(io.rows[2], lu0[2 * TA], ej, K, ctl, eqm + axis * LPA, c_scale / rhobar);
   }
   // G thread (v, h); the h = 0 thread is the variable thread of v
   int v, h;
@@ -1020,7 +1179,8 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
     // one out-of-line call per check interval; before its LAST iteration the block captures the multipliers
     // y = rho (w - clip(w)) of the thread's rows (io.yo) for the delta y of the check
-    if constexpr (L::VMAJOR) qpd_block5<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
+    if constexpr (L::ROWFULL) qpd_block1<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
+    else if constexpr (L::VMAJOR) qpd_block5<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     else if constexpr (L::NCH == 4) qpd_block4<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     else qpd_block<KC>(io, smx, ta, it_end - it + 1, o.alpha, sync_cta);
     iters = it_end;
@@ -1031,22 +1191,20 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     qpd_check<KC>(a, slot, tid, smem, io, sync_cta);
     // V must hold v = rho (2 clip(w) - w) again for the next iteration
 #pragma unroll
-    for (int r = 0; r < 3; r++)
+    for (int r = 0; r < L::NSLOT; r++)
       if (io.rows[r].meta & 8) vv[io.rows[r].voff] = io.rows[r].rho * (2.0 * io.rows[r].p - io.rows[r].w);
     sync_cta();
   }
   state = io.state;
   rhobar = io.rhobar;
-  const QpdRow &ra = io.rows[0], &rb = io.rows[1], &rj = io.rows[2];
   const double xv = io.xv;
   double *xr = smx + L::O_XR;
 
   // ---------------- hand the iterate back to the lane-per-segment layout: W slots, rho, x ----------------
   {
     double *ctlw = smx + L::O_CTRL;
-    qpd_handback_row(ra, K, ctlw, STR);
-    qpd_handback_row(rb, K, ctlw, STR);
-    qpd_handback_row(rj, K, ctlw, STR);
+#pragma unroll
+    for (int sl = 0; sl < L::NSLOT; sl++) qpd_handback_row(io.rows[sl], K, ctlw, STR);
     if (isvar) xr[QPD_CP + v] = xv;
   }
   sync_cta();

@@ -109,7 +109,8 @@ struct QpdLayout {
   static constexpr int O_VCF = O_CE + 18 * KC;                       // continuity gather coefficients [N][3]
   static constexpr int O_LU = ((O_VCF + 3 * N + 1) / 2) * 2;         // (l, u) of the row slots [NSLOT][TA] pairs (16-byte aligned)
   static constexpr int O_PS = O_LU + 2 * NSLOT * TA;                 // v-major layout: partial sums of x~ [NCH][N]
-  static constexpr int AXIS = O_PS + (VMAJOR ? ((NCH * N + 1) / 2) * 2 : 0);  // doubles per axis (even)
+  static constexpr int O_V2 = O_PS + (VMAJOR ? ((NCH * N + 1) / 2) * 2 : 0);  // second row-value array (checks: y next to delta y)
+  static constexpr int AXIS = O_V2 + ((QPD_VB * (KC + 1) + 1) / 2) * 2;       // doubles per axis (even)
   // per-CTA tail: reduction scratch [NWARPS][QPD_NRED], eqmask ints [2][LPA]
   static constexpr int O_RED = 2 * AXIS;
   static constexpr int O_EQ = O_RED + NWARPS * QPD_NRED;
@@ -1026,28 +1027,32 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
   int state = io.state;
   const int it = io.it;
 
+  // value copies of the row slots: the shared-memory stores below go through generic pointers, and with the slots read
+  // through `io` (local memory) every one of them forces the fields to be re-loaded
+  QpdRow rows[NS];
+  double yo_[NS];
+  QpdLU lus[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) { rows[sl] = io.rows[sl]; yo_[sl] = io.yo[sl]; lus[sl] = lu0[sl * TA]; }
   double red_v[QPD_NRED];
 #pragma unroll
   for (int i = 0; i < QPD_NRED; i++) red_v[i] = 0.0;
   const double c_over_rhobar = c_scale / rhobar;
-  // delta y of this iteration -> V (for A' delta y), its norm and the support-function term of the certificate
+  // One pass: delta y -> V and y -> V2 (and the relaxed x -> XR), ONE barrier, then both gathers A' delta y and A' y, P x
+  // and the row residuals as independent instruction streams.
+  double *vv2 = smx + L::O_V2;
 #pragma unroll
-  for (int sl = 0; sl < NS; sl++) qpd_check_dy(io.rows[sl], lu0[sl * TA], io.yo[sl], vv, c_scale, c_over_rhobar, red_v);
-  sync_cta();
-  double cDv = 0.0;
-  if (isvar) {
-    if (vk < K) cDv = lsx[QPD_LS * vk + 15 + vj];
-    const double atd = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
-    red_v[8] = fabs(cDv * atd);
-    xr[QPD_CP + v] = xv;
+  for (int sl = 0; sl < NS; sl++) {
+    const QpdRow &r = rows[sl];
+    qpd_check_dy(r, lus[sl], yo_[sl], vv, c_scale, c_over_rhobar, red_v);
+    if (r.meta & 8) vv2[r.voff] = r.rho * (r.w - r.p);  // y
   }
-  sync_cta();
-#pragma unroll
-  for (int sl = 0; sl < NS; sl++)
-    if (io.rows[sl].meta & 8) vv[io.rows[sl].voff] = io.rows[sl].rho * (io.rows[sl].w - io.rows[sl].p);  // y
+  if (isvar) xr[QPD_CP + v] = xv;
   sync_cta();
   if (isvar) {
-    const double aty = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
+    const double cDv = vk < K ? lsx[QPD_LS * vk + 15 + vj] : 0.0;
+    const double atd = qpd_gather(vb, vkk, vj, tkv, vcf[0], vcf[1], vcf[2]);
+    const double aty = qpd_gather(vb + (L::O_V2 - L::O_V), vkk + (L::O_V2 - L::O_V), vj, tkv, vcf[0], vcf[1], vcf[2]);
     double px = 0.0;
     const double *pk = ctl + QP_SM_P * STR + vk;
 #pragma unroll
@@ -1056,13 +1061,14 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
       px += pk[e * STR] * xr[QPD_CP + 6 * vk + i];
     }
     if (vk >= K) px = 0.0;
+    red_v[8] = fabs(cDv * atd);
     red_v[1] = cDv * fabs(px + qv + aty);
     red_v[4] = cDv * fabs(qv);
     red_v[5] = cDv * fabs(px);
     red_v[6] = cDv * fabs(aty);
   }
 #pragma unroll
-  for (int sl = 0; sl < NS; sl++) qpd_check_resid(io.rows[sl], qpd_row_eval<KC>(io.rows[sl], xr, smx), c_over_rhobar, red_v);
+  for (int sl = 0; sl < NS; sl++) qpd_check_resid(rows[sl], qpd_row_eval<KC>(rows[sl], xr, smx), c_over_rhobar, red_v);
   qpd_reduce(red_v, red, warp, lane, L::NWARPS, sync_cta);
   const double pri = red_v[0], dua = red_v[1], nz = red_v[2], nax = red_v[3], nq = red_v[4], npx = red_v[5], naty = red_v[6];
   const double nd = red_v[7], na = red_v[8], lhs = red_v[9];
@@ -1080,7 +1086,7 @@ SP_DEV_NOINLINE void qpd_check(const QpArgs &a, int slot, int tid, double *smem,
       const double ratio = est / rhobar;
       double *ctlw = smx + L::O_CTRL;
 #pragma unroll
-      for (int sl = 0; sl < NS; sl++) qpd_rescale_row(io.rows[sl], ratio, K, ctlw + QP_SM_RHO * STR, STR);
+      for (int sl = 0; sl < NS; sl++) { qpd_rescale_row(rows[sl], ratio, K, ctlw + QP_SM_RHO * STR, STR); io.rows[sl].w = rows[sl].w; io.rows[sl].rho = rows[sl].rho; }
       rhobar = est;
       sync_cta();
       if (warp == 0) qpd_control_refactor<KC>(a, slot, lane, smem, c_scale, rhobar);
@@ -1115,7 +1121,7 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
   int state = QP_RUNNING;
   if (warp == 0) qpd_control_setup<KC>(a, slot, lane, smem);
   // zero the padded arrays of the fast layout (V incl. pads and the extra block, C / XR incl. pads)
-  for (int i = ta; i < QPD_VB * (KC + 1); i += TA) smx[L::O_V + i] = 0.0;
+  for (int i = ta; i < QPD_VB * (KC + 1); i += TA) { smx[L::O_V + i] = 0.0; smx[L::O_V2 + i] = 0.0; }
   for (int i = ta; i < N + 8; i += TA) { smx[L::O_C + i] = 0.0; smx[L::O_XR + i] = 0.0; }
   sync_cta();
   c_scale = red[0];

@@ -197,7 +197,7 @@ struct QpdRow {
   int coff;                // offset of the stencil window in C / XR
   int voff;                // offset of this row's value in V
   int meta;                // bits 0-1 difference order, bit 3 valid, bit 4 equality row, bits 8-15 segment, 16.. row in slots (r)
-  double er;               // Ruiz row scaling E_r = sqrt(rho_r c / (rhobar eqfac)): invariant under adaptive rho (checks only)
+  double er, ier;          // Ruiz row scaling E_r = sqrt(rho_r c / (rhobar eqfac)) and 1 / E_r: invariant under adaptive rho (checks only)
 };
 
 // Chunk h of row v of G = S^-1: the NCH threads (v, 0..NCH-1), adjacent lanes, run the block forward / backward
@@ -504,6 +504,7 @@ SP_DEV void qpd_init_diff(QpdRow &r, QpdLU &lu, int e, int K, const double *ctl,
   lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
   r.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
   r.er = sqrt(r.rho * c_over_rhobar * (eq ? 1e-3 : 1.0));
+  r.ier = r.er > 0.0 ? 1.0 / r.er : 0.0;
 }
 
 // initial state of a continuity / initial-state row slot: ej = row index in [0, 3 KC) or < 0 (no row)
@@ -526,6 +527,7 @@ SP_DEV void qpd_init_join(QpdRow &rj, QpdLU &lu, int ej, int K, const double *ct
   lu.u = live ? ctl[QP_SM_U * STR + ooff] : 1.0;
   rj.rho = live ? ctl[QP_SM_RHO * STR + ooff] : 0.0;
   rj.er = sqrt(rj.rho * c_over_rhobar * (eq ? 1e-3 : 1.0));
+  rj.ier = rj.er > 0.0 ? 1.0 / rj.er : 0.0;
 }
 // a row slot of the unified numbering: [0, NN) difference rows, [NN, ROWS) continuity / initial-state rows, else none
 template <int KC>
@@ -554,8 +556,7 @@ SP_DEV void qpd_check_dy(const QpdRow &r, const QpdLU &b, double yo, double *vv,
   const double dy = r.rho * (r.w - r.p) - yo;
   vv[r.voff] = dy;
   if (r.rho > 0.0) {
-    const double Er = r.er;
-    red_v[7] = qpd_max(red_v[7], fabs(c_scale * dy / Er));
+    red_v[7] = qpd_max(red_v[7], fabs(c_scale * dy * r.ier));
     red_v[9] += c_scale * (b.u * qpd_max(dy, 0.0) + b.l * (dy < 0.0 ? dy : 0.0));
   }
 }
@@ -570,7 +571,7 @@ SP_DEV void qpd_check_resid(const QpdRow &r, double ax, double c_over_rhobar, do
 // adaptive rho: keep (z, y), w' = z + y / rho'; publish the new rho in the lane-per-segment RHO slots
 SP_DEV void qpd_rescale_row(QpdRow &r, double ratio, int K, double *ctl_rho, int str) {
   if (!(r.meta & 8)) return;
-  r.w = r.p + (r.w - r.p) / ratio;
+  r.w = r.p + (r.w - r.p) / ratio;  // (rare: only when rho is re-tuned)
   r.rho *= ratio;
   const int k = (r.meta >> 8) & 0xff;
   if (k < K) ctl_rho[(r.meta >> 16) * str + k] = r.rho;
@@ -1196,9 +1197,18 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     io.it = iters;
     qpd_check<KC>(a, slot, tid, smem, io, sync_cta);
     // V must hold v = rho (2 clip(w) - w) again for the next iteration
+    {  // (values first, stores after: the stores go through generic pointers and would force `io` to be re-read)
+      double vnew[L::NSLOT];
+      int voffs[L::NSLOT];
 #pragma unroll
-    for (int r = 0; r < L::NSLOT; r++)
-      if (io.rows[r].meta & 8) vv[io.rows[r].voff] = io.rows[r].rho * (2.0 * io.rows[r].p - io.rows[r].w);
+      for (int r = 0; r < L::NSLOT; r++) {
+        vnew[r] = io.rows[r].rho * (2.0 * io.rows[r].p - io.rows[r].w);
+        voffs[r] = (io.rows[r].meta & 8) ? io.rows[r].voff : -1;
+      }
+#pragma unroll
+      for (int r = 0; r < L::NSLOT; r++)
+        if (voffs[r] >= 0) vv[voffs[r]] = vnew[r];
+    }
     sync_cta();
   }
   state = io.state;

@@ -651,7 +651,7 @@ SP_DEV_NOINLINE void qpd_block(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> &
       const double g2a = vb[QPD_V2 + vj - 2], g2b = vb[QPD_V2 + vj - 1], g2c = vb[QPD_V2 + vj];
       const double g3a = vb[QPD_V3 + vj - 3], g3b = vb[QPD_V3 + vj - 2], g3c = vb[QPD_V3 + vj - 1], g3d = vb[QPD_V3 + vj];
       const double c0 = vkk[QPD_VC], c1 = vkk[QPD_VC + 1], c2 = vkk[QPD_VC + 2];
-      const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];
+      const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];  // (hoisting these into registers too costs more than it saves: 10.5 -> 11.4 ms)
       qpd_sched_fence_if<QPD_STAGE_ROWS(KC)>();
       double g = tkv * g0;
       g += 5.0 * (g1a - g1b);
@@ -921,6 +921,10 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
   double G[N];
 #pragma unroll
   for (int e = 0; e < N; e++) G[e] = io.G[e];
+  const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];  // continuity gather coefficients: constants of the block
+  QpdLU lub[NS];                                          // and the (l, u) pairs of the row slots
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) lub[sl] = lu0[sl * TA];
   double yo[NS];
 #pragma unroll
   for (int sl = 0; sl < NS; sl++) yo[sl] = 0.0;
@@ -934,7 +938,6 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
       const double g2a = vb[QPD_V2 + vj - 2], g2b = vb[QPD_V2 + vj - 1], g2c = vb[QPD_V2 + vj];
       const double g3a = vb[QPD_V3 + vj - 3], g3b = vb[QPD_V3 + vj - 2], g3c = vb[QPD_V3 + vj - 1], g3d = vb[QPD_V3 + vj];
       const double c0 = vkk[QPD_VC], c1 = vkk[QPD_VC + 1], c2 = vkk[QPD_VC + 2];
-      const double f0 = vcf[0], f1 = vcf[1], f2 = vcf[2];
       qpd_sched_fence();
       const double t01 = tkv * g0 + 5.0 * (g1a - g1b);
       const double t2 = 20.0 * ((g2a - g2b) - (g2b - g2c));
@@ -965,14 +968,11 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
     sync_cta();
     {  // S1
       double win[ND > 0 ? ND : 1][4];
-      QpdLU lub[NS];
 #pragma unroll
       for (int sl = 0; sl < ND; sl++) {
         const double *cp = cx + r[sl].coff;
         win[sl][0] = cp[0]; win[sl][1] = cp[1]; win[sl][2] = cp[2]; win[sl][3] = cp[3];
       }
-#pragma unroll
-      for (int sl = 0; sl < NS; sl++) lub[sl] = lu0[sl * TA];
       qpd_sched_fence();
 #pragma unroll
       for (int sl = 0; sl < ND; sl++) {

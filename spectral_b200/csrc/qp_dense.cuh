@@ -91,10 +91,12 @@ struct QpdLayout {
   static constexpr bool TWO_SLOTS = NCH == 2;
   static constexpr int T0 = TWO_SLOTS ? ((NJ + 31) / 32) * 32 : 0;
   static constexpr int TN = TA - T0;
-  // row slots per thread.  Legacy layouts: 3 (difference rows A, B and one continuity row J).  Full-row layout: slot s of
-  // thread t holds row s TA + t of the unified numbering [0, NN) difference rows, [NN, ROWS) continuity / init rows.
-  static constexpr int NSLOT = ROWFULL ? (ROWS + TA - 1) / TA : 3;
-  static_assert(ROWFULL ? (NSLOT * TA >= ROWS) : (TWO_SLOTS ? (2 * TN + T0 >= NN) : (TA >= ROWS)), "row slots");
+  // row slots per thread.  Legacy layouts: 3 (difference rows A, B and one continuity row J).  Full-row layout: NDS slots of
+  // difference rows and NJS slots of continuity / init rows, so that every slot is one kind of row on all threads.
+  static constexpr int NDS = (NN + TA - 1) / TA;   // full-row layout: slots of difference rows (slot s = row s TA + t) ...
+  static constexpr int NJS = (NJ + TA - 1) / TA;   // ... followed by slots of continuity / initial-state rows
+  static constexpr int NSLOT = ROWFULL ? NDS + NJS : 3;
+  static_assert(ROWFULL || (TWO_SLOTS ? (2 * TN + T0 >= NN) : (TA >= ROWS)), "row slots");
   static constexpr int LPA = KC <= 8 ? 8 : 16; // lanes per axis of the lane-per-segment (control) code
   static constexpr int STR = LPA;              // its shared-memory stride
   // per-axis shared memory (doubles)
@@ -900,7 +902,7 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
   static_assert(L::ROWFULL && L::NCH == 1 && N % 4 == 0, "full-row layout");
   constexpr int GRP = 12;  // doubles of g in flight per group (6 LDS.128)
   static_assert(N % GRP == 0, "g in whole groups");
-  constexpr int ND = NN / TA;  // slots 0 .. ND-1 hold difference rows on every thread
+  constexpr int ND = L::NDS;   // slots 0 .. ND-1 hold difference rows, slots ND .. NS-1 continuity / initial-state rows
   const int v = ta;
   const bool isg = v < N;
   const int vk = isg ? v / 6 : 0, vj = isg ? v - 6 * vk : 0;
@@ -966,26 +968,33 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
       }
     }
     sync_cta();
-    {  // S1
-      double win[ND > 0 ? ND : 1][4];
+    {  // S1: every slot is one kind of row on all threads -> one straight-line stream: loads, fence, updates
+      double win[ND][4], jw[NS - ND][6], jc[NS - ND][6];
 #pragma unroll
       for (int sl = 0; sl < ND; sl++) {
         const double *cp = cx + r[sl].coff;
         win[sl][0] = cp[0]; win[sl][1] = cp[1]; win[sl][2] = cp[2]; win[sl][3] = cp[3];
+      }
+#pragma unroll
+      for (int sl = ND; sl < NS; sl++) {
+        const double *cp = cx + r[sl].coff;
+        const double *ce = smx + L::O_CE + 6 * (3 * ((r[sl].meta >> 8) & 0xff) + (((r[sl].meta >> 16) & 0xff) - 18 > 0 ? ((r[sl].meta >> 16) & 0xff) - 18 : 0));
+#pragma unroll
+        for (int m = 0; m < 6; m++) { jw[sl - ND][m] = cp[m]; jc[sl - ND][m] = ce[m]; }
       }
       qpd_sched_fence();
 #pragma unroll
       for (int sl = 0; sl < ND; sl++) {
         const double zt = qpd_diff_row(win[sl], r[sl].meta & 3, r[sl].scale);
         const double u = qpd_row_update(r[sl], lub[sl], zt, alpha);
-        vv[r[sl].voff] = u;  // every thread has a row in these slots
+        if (r[sl].meta & 8) vv[r[sl].voff] = u;
       }
 #pragma unroll
       for (int sl = ND; sl < NS; sl++) {
-        if (r[sl].meta & 8) {
-          const double zt = qpd_row_eval<KC>(r[sl], cx, smx);
-          vv[r[sl].voff] = qpd_row_update(r[sl], lub[sl], zt, alpha);
-        }
+        const double *w6 = jw[sl - ND], *c6 = jc[sl - ND];
+        const double zt = (c6[0] * w6[0] + c6[1] * w6[1]) + (c6[2] * w6[2] + c6[3] * w6[3]) + (c6[4] * w6[4] + c6[5] * w6[5]);
+        const double u = qpd_row_update(r[sl], lub[sl], zt, alpha);
+        if (r[sl].meta & 8) vv[r[sl].voff] = u;
       }
     }
     sync_cta();
@@ -1136,8 +1145,10 @@ SP_DEV void qpd_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
   QpdLU *lu0 = (QpdLU *)(smx + L::O_LU) + ta;  // bounds of this thread's row slots: lu0[s * TA]
   if constexpr (L::ROWFULL) {
 #pragma unroll
-    for (int sl = 0; sl < L::NSLOT; sl++)
-      qpd_init_row<KC>(io.rows[sl], lu0[sl * TA], sl * TA + ta, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+    for (int sl = 0; sl < L::NSLOT; sl++) {
+      if (sl < L::NDS) qpd_init_diff<KC>(io.rows[sl], lu0[sl * TA], sl * TA + ta < L::NN ? sl * TA + ta : -1, K, ctl, lsx, eqm + axis * LPA, c_scale / rhobar);
+      else qpd_init_join<KC>(io.rows[sl], lu0[sl * TA], (sl - L::NDS) * TA + ta, K, ctl, eqm + axis * LPA, c_scale / rhobar);
+    }
   } else {
     int ea, eb, ej;
     if (L::TWO_SLOTS) {

@@ -63,6 +63,8 @@
 // every lane on the same address (one wavefront per LDS.128), the gather runs on all variable lanes, and every thread
 // carries ceil(21 KC / 64) constraint rows whose loads and updates interleave (ILP instead of TLP: the kernel is
 // latency-bound and every wider layout tried lost to its extra barriers and instructions, profiles/r1_qpd_staging.md).
+// Measured (profiles/r1_qpd_staging.md): K <= 10: 9.95 ms (row pairs at 128 registers) -> 8.05 ms; K <= 8: 10.6 ms, a tie with the
+// staged row-pair layout at 168 registers (10.5 - 10.8 ms), which is kept there.
 #ifndef QPD_ROWFULL
 #define QPD_ROWFULL(KC) ((KC) == 10)
 #endif

@@ -15,7 +15,14 @@
 // their rows are finite-difference stencils of the control points (solve_3d.cc:823-949), applied from
 // zero-padded shared-memory arrays so that every thread runs the same instruction stream.
 //
-// Thread map (per axis TA = 2n threads rounded up to whole warps: 96 for KC = 8; CTA = 2 TA):
+// Three thread layouts, each the measured winner of its class (profiles/r1_qpd_staging.md):
+//   KC = 8        row pairs (below): 2 chunks per row of G, 96 threads per axis, 168 registers, staged loads   qpd_block
+//   KC = 10       full rows: one thread per variable holds its whole row of G, 64 threads per axis, 255
+//                 registers, four generic row slots per thread                                              qpd_block1
+//   KC = 12, 16   quarter rows: 4 chunks per row, one constraint row per thread, 288 / 384 threads per axis  qpd_block4
+// (QPD_VMAJOR / qpd_block5 is a fourth, measured slower and kept off.)
+//
+// Thread map of the row-pair layout (per axis TA = 2n threads rounded up to whole warps: 96 for KC = 8; CTA = 2 TA):
 //   thread (v, h) = ta >> 1, ta & 1 : half row h of G (n/2 doubles in registers); the h = 0 thread also owns the
 //                                     relaxed iterate x_v, gathers (A' v)_v and publishes x~_v
 //   row slots                       : every thread owns up to two "difference" rows (containment, velocity,

@@ -128,7 +128,9 @@ struct QpdLayout {
   // with LPA = 8 the upper half of warp 0 holds no problem: its lanes run the lane-per-segment code on a
   // scratch copy of the control slots so that they never touch the real ones
   static constexpr int O_DUMMY = O_EQ + LPA;  // (2 * LPA ints before it)
-  static constexpr int TOTAL = O_DUMMY + (2 * LPA < 32 ? QP_SM_DOUBLES_PER_LANE * STR : 0);
+  // one scratch copy per idle lane group (32 / LPA - 2 of them), so that no two threads ever touch the same address
+  static constexpr int DUMMY_GROUPS = 2 * LPA < 32 ? 32 / LPA - 2 : 0;
+  static constexpr int TOTAL = O_DUMMY + DUMMY_GROUPS * QP_SM_DOUBLES_PER_LANE * STR;
   static constexpr int BYTES = TOTAL * 8;
 };
 
@@ -386,7 +388,7 @@ SP_DEV_NOINLINE void qpd_control_setup(const QpArgs &a, int slot, int lane, doub
   int *eqm = (int *)(smem + L::O_EQ);
   const int cgrp = lane / LPA, cseg = lane % LPA, caxis = cgrp & 1;
   const bool creal = lane < JW;  // lanes beyond the two axis groups idle on scratch slots
-  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY;
+  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY + (cgrp - 2) * QP_SM_DOUBLES_PER_LANE * STR;
   double *cfs = smem + caxis * L::AXIS + L::O_FS;
   double *cls = smem + caxis * L::AXIS + L::O_LS;
   int *ceq = eqm + caxis * LPA;
@@ -426,7 +428,7 @@ SP_DEV_NOINLINE void qpd_control_refactor(const QpArgs &a, int slot, int lane, d
   int *eqm = (int *)(smem + L::O_EQ);
   const int cgrp = lane / LPA, cseg = lane % LPA, caxis = cgrp & 1;
   const bool creal = lane < JW;  // lanes beyond the two axis groups idle on scratch slots
-  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY;
+  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY + (cgrp - 2) * QP_SM_DOUBLES_PER_LANE * STR;
   double *cfs = smem + caxis * L::AXIS + L::O_FS;
   double *cls = smem + caxis * L::AXIS + L::O_LS;
   int *ceq = eqm + caxis * LPA;
@@ -448,7 +450,7 @@ SP_DEV_NOINLINE void qpd_control_finish(const QpArgs &a, int slot, int lane, dou
   int *eqm = (int *)(smem + L::O_EQ);
   const int cgrp = lane / LPA, cseg = lane % LPA, caxis = cgrp & 1;
   const bool creal = lane < JW;  // lanes beyond the two axis groups idle on scratch slots
-  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY;
+  double *smc = creal ? smem + caxis * L::AXIS + L::O_CTRL : smem + L::O_DUMMY + (cgrp - 2) * QP_SM_DOUBLES_PER_LANE * STR;
   double *cfs = smem + caxis * L::AXIS + L::O_FS;
   double *cls = smem + caxis * L::AXIS + L::O_LS;
   int *ceq = eqm + caxis * LPA;

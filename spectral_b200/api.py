@@ -22,7 +22,7 @@ import numpy as np
 from .wire import ScenarioBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("SPECTRAL_LIB_DIR") or os.path.join(_HERE, "lib")  # override: kernel experiments built out of tree
 
 TRP, CUB = 0, 1
 VARIANT_ID = {"trp": TRP, "cub": CUB, TRP: TRP, CUB: CUB}

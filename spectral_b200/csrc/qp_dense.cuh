@@ -16,10 +16,11 @@
 // zero-padded shared-memory arrays so that every thread runs the same instruction stream.
 //
 // Three thread layouts, each the measured winner of its class (profiles/r1_qpd_staging.md):
-//   KC = 8        row pairs (below): 2 chunks per row of G, 96 threads per axis, 168 registers, staged loads   qpd_block
+//   KC = 8, 12    row pairs (below): 2 chunks per row of G, 96 / 160 threads per axis, 168 registers, staged     qpd_block
 //   KC = 10       full rows: one thread per variable holds its whole row of G, 64 threads per axis, 255
 //                 registers, four generic row slots per thread                                              qpd_block1
-//   KC = 12, 16   quarter rows: 4 chunks per row, one constraint row per thread, 288 / 384 threads per axis  qpd_block4
+//   KC = 16       quarter rows: 4 chunks per row, one constraint row per thread, 384 threads per axis        qpd_block4
+//                 (KC = 12 ran this layout at 7.7 ms; as staged row pairs, one CTA per SM at 320 threads: 6.4 ms)
 // (QPD_VMAJOR / qpd_block5 is a fourth, measured slower and kept off.)
 //
 // Thread map of the row-pair layout (per axis TA = 2n threads rounded up to whole warps: 96 for KC = 8; CTA = 2 TA):
@@ -76,7 +77,7 @@
 #define QPD_ROWFULL(KC) ((KC) == 10)
 #endif
 #ifndef QPD_NCH
-#define QPD_NCH(KC) (QPD_ROWFULL(KC) ? 1 : (((KC) >= 12 || QPD_VMAJOR(KC)) ? 4 : 2))
+#define QPD_NCH(KC) (QPD_ROWFULL(KC) ? 1 : (((KC) >= 16 || QPD_VMAJOR(KC)) ? 4 : 2))
 #endif
 SP_HD constexpr int qpd_nch(int KC) { return QPD_NCH(KC); }
 
@@ -147,16 +148,16 @@ SP_DEV void qpd_lds2(const double *p, double &a, double &b) {
 // the register budget has room (KC <= 8: 168 registers, measured 14.9 -> 12.5 ms) and spill where it has not (KC = 10 at
 // 128 registers: 9.5 -> 12.2 ms; KC >= 12 at 96 / 80: 8.0 -> 8.9 ms) -- profiles/r1_qpd_staging.md.
 #ifndef QPD_STAGE
-#define QPD_STAGE(KC) ((KC) <= 8)      // S3: the whole g chunk in flight (CH doubles of temporaries)
+#define QPD_STAGE(KC) ((KC) <= 8 || (KC) == 12)      // S3: the whole g chunk in flight (CH doubles of temporaries)
 #endif
 #ifndef QPD_STAGE_GROUP
 #define QPD_STAGE_GROUP(KC) 0  // S3 in groups of this many doubles where the whole chunk does not fit (0: unstaged; KC = 10 in groups of 10: 9.65 -> 10.2 ms)
 #endif
 #ifndef QPD_LU_REG
-#define QPD_LU_REG(KC) ((KC) <= 8)   // (l, u) of the row slots in registers instead of one LDS.128 per slot and iteration
+#define QPD_LU_REG(KC) ((KC) <= 8 || (KC) == 12)   // (l, u) of the row slots in registers instead of one LDS.128 per slot and iteration
 #endif
 #ifndef QPD_STAGE_ROWS
-#define QPD_STAGE_ROWS(KC) ((KC) <= 8)   // S2 / S1: 13 - 18 doubles of temporaries (KC = 10 at 128 registers: 9.5 -> 10.6 ms)
+#define QPD_STAGE_ROWS(KC) ((KC) <= 8 || (KC) == 12)   // S2 / S1: 13 - 18 doubles of temporaries (KC = 10 at 128 registers: 9.5 -> 10.6 ms)
 #endif
 template <bool ON>
 SP_DEV void qpd_sched_fence_if() {

@@ -16,8 +16,8 @@
 // zero-padded shared-memory arrays so that every thread runs the same instruction stream.
 //
 // Three thread layouts, each the measured winner of its class (profiles/r1_qpd_staging.md):
-//   KC = 8, 12    row pairs (below): 2 chunks per row of G, 96 / 160 threads per axis, 168 registers, staged     qpd_block
-//   KC = 10       full rows: one thread per variable holds its whole row of G, 64 threads per axis, 255
+//   KC = 12       row pairs (below): 2 chunks per row of G, 160 threads per axis, 168 registers, staged loads  qpd_block
+//   KC = 8, 10    full rows: one thread per variable holds its whole row of G, 64 threads per axis, 255
 //                 registers, four generic row slots per thread                                              qpd_block1
 //   KC = 16       quarter rows: 4 chunks per row, one constraint row per thread, 384 threads per axis        qpd_block4
 //                 (KC = 12 ran this layout at 7.7 ms; as staged row pairs, one CTA per SM at 320 threads: 6.4 ms)
@@ -71,10 +71,10 @@
 // every lane on the same address (one wavefront per LDS.128), the gather runs on all variable lanes, and every thread
 // carries ceil(21 KC / 64) constraint rows whose loads and updates interleave (ILP instead of TLP: the kernel is
 // latency-bound and every wider layout tried lost to its extra barriers and instructions, profiles/r1_qpd_staging.md).
-// Measured (profiles/r1_qpd_staging.md): K <= 10: 9.95 ms (row pairs at 128 registers) -> 8.05 ms; K <= 8: 10.6 ms, a tie with the
-// staged row-pair layout at 168 registers (10.5 - 10.8 ms), which is kept there.
+// Measured (profiles/r1_qpd_staging.md): K <= 10: 9.95 ms (row pairs at 128 registers) -> 7.85 ms; K <= 8: 10.0 ms against 10.6 ms
+// of the staged row-pair layout at 168 registers (same box), once g is staged in groups of 24 doubles.
 #ifndef QPD_ROWFULL
-#define QPD_ROWFULL(KC) ((KC) == 10)
+#define QPD_ROWFULL(KC) ((KC) <= 10)
 #endif
 #ifndef QPD_NCH
 #define QPD_NCH(KC) (QPD_ROWFULL(KC) ? 1 : (((KC) >= 16 || QPD_VMAJOR(KC)) ? 4 : 2))
@@ -913,7 +913,7 @@ SP_DEV_NOINLINE void qpd_block1(QpdIOT<QpdLayout<KC>::CH, QpdLayout<KC>::NSLOT> 
   constexpr int N = L::N, TA = L::TA, NS = L::NSLOT, NN = L::NN;
   static_assert(L::ROWFULL && L::NCH == 1 && N % 4 == 0, "full-row layout");
   // doubles of g in flight per group: KC = 10 measured 8.05 ms with 12, 7.85 ms with 20, 8.2 ms with 30 (spills)
-  constexpr int GRP = (N % 20 == 0) ? 20 : 12;
+  constexpr int GRP = (N % 24 == 0) ? 24 : ((N % 20 == 0) ? 20 : 12);  // (KC = 8: 10.57 ms with 12, 10.0 ms with 24)
   static_assert(N % GRP == 0, "g in whole groups");
   constexpr int ND = L::NDS;   // slots 0 .. ND-1 hold difference rows, slots ND .. NS-1 continuity / initial-state rows
   const int v = ta;

@@ -362,9 +362,9 @@ def run_ours(args):
                          "achieved": achieved_tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the k_qpd<8> launch of one 1024-scenario step
-                         # (703 live CTAs; ncu --set full, profiles/r1_qpd_full.md: 8.1 MB read + 39.9 MB written): stack/local-memory write-back, the
+                         # (703 live CTAs; ncu --set full, profiles/r1_qpd_full.md: 3.2 MB read + 19.2 MB written): stack/local-memory write-back, the
                          # ADMM state itself never leaves shared memory and registers
-                         "traffic": 47.9e6,
+                         "traffic": 22.4e6,
                          "peak_source": "FP64 FMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "ms_per_launch_group": qp_ms, "flops_per_step": flops_per_step,
                          "note": "timed on one stream (pass A, %d steps) with CUDA events around the QP stage; the headline value overlaps %d steps" % (na, NS)},

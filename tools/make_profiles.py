@@ -45,7 +45,7 @@ for i in hot:
         h1 = i
 st = [hdr.index(k) for k in ("stall_barrier", "stall_short_sb", "stall_wait", "stall_long_sb", "stall_branch_resolving", "stall_math", "stall_not_selected", "stall_mio")]
 rng = range(h0, h1 + 1)
-lines = ["# r1 FINAL k_qpd<8> hot loop (qpd_block: one ADMM iteration = S2 gather | S3 G.g | S1 row updates, 3 CTA barriers): ncu source page, per SASS instruction", "",
+lines = ["# r1 FINAL k_qpd<8> hot loop (qpd_block1, full-row layout: one ADMM iteration = S2 gather | S3 G.g | S1 row updates, 3 CTA barriers): ncu source page, per SASS instruction", "",
          "Capture: `ncu --set full --clock-control none --import-source on -k regex:k_qpd -c 3 python tools/profile_step.py 1024 1`, launch 0 (final kernel of the round).",
          "The loop holds %.0f %% of the kernel's executed warp-instructions, %.0f %% of its stall samples and %.0f %% of its shared-memory wavefronts (the rest: termination check every 25 iterations, block entry/exit, setup, polish)." % (
              100 * sum(I(data[i][iex]) for i in rng) / tot, 100 * sum(I(data[i][ismp]) for i in rng) / ts, 100 * sum(I(data[i][iw]) for i in rng) / tw),

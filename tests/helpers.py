@@ -198,6 +198,13 @@ def assert_batch_parity(got, ref, label="", need_verified_frac=0.0, ref0=None, m
     ok_ref = st0 <= 1
     decided = decided_classes(ref, ref0)
     mism = got.ok() != ok_ref
+    # "solved inaccurate" AT the iteration cap is a threshold test (10 x eps) on a non-converged iterate: whether the last
+    # iterate of an infeasible or very slowly converging problem squeezes under it depends on rounding-level details of
+    # the iterate path -- the reference-settings oracle itself accepts 160 provably infeasible config-2 scenarios this way
+    # (DESIGN.md 6.1).  Such outcomes are borderline on either side and count as undecided (about 1 in 1000 scenarios).
+    cap = 5000
+    borderline = ((got.status == 1) & (got.iters >= cap)) | ((st0 == 1) & (ref0["iters"] >= cap))
+    decided = decided & ~borderline
     hard = mism & decided
     assert hard.sum() <= max_status_mismatch, "%s: solved/failed class differs at %d decided scenarios %s (got %s, ref %s)" % (
         label, hard.sum(), np.nonzero(hard)[0][:8], got.status[hard][:8], st0[hard][:8])

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""tools/parity_sweep.py -- the parity policy of tests/helpers.py on more batches than the test-suite runs: config-2 shards
+beyond the first, trapezoid-prism batches with other seeds, config 3 with other group counts.  Prints one line per batch."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import helpers as H
+from spectral_b200 import api
+from spectral_b200.scenarios import GOLDEN_W_CUB, GOLDEN_W_TRP, WEIGHTS_FILE, config2, config3, load_fixture, perturbed_obstacles
+
+p = api.SpectralPlanner(device=0, max_batch=1024, n_max=128, r_max=8, k_max=32)
+cases = [("cub", config2(1024, first=1024 * i), GOLDEN_W_CUB, "config2 shard %d" % i) for i in (1, 2, 3)]
+cases += [("trp", perturbed_obstacles(load_fixture("c1"), 512, seed=s), GOLDEN_W_TRP, "trp c1 seed %d" % s) for s in (101, 202)]
+cases += [("trp", config3(512, groups=g, first=4096), WEIGHTS_FILE, "config3 groups %d" % g) for g in (1, 64)]
+cases += [("cub", perturbed_obstacles(load_fixture("c3"), 512, seed=303), WEIGHTS_FILE, "cub c3 seed 303")]
+bad = 0
+for variant, batch, w, name in cases:
+    t = time.time()
+    got = p.solve(variant, batch, w)
+    ref, ref0 = H.oracle_pair(variant, batch, w)
+    try:
+        both = H.assert_batch_parity(got, ref, name, need_verified_frac=0.4, ref0=ref0, batch=batch, variant=variant, weights=w)
+        print("%-20s B=%4d ok %4d verified %4d compared %4d  PASS  (%.0f s)" % (name, batch.batch, got.ok().sum(), got.verified().sum(), both.sum(), time.time() - t))
+    except AssertionError as e:
+        bad += 1
+        print("%-20s FAIL: %s" % (name, str(e)[:300]))
+print("failures:", bad)

@@ -61,6 +61,9 @@ def have_reference():
 def solve_batch(variant, batch, weights, mode=0, k_max=32, nthreads=1, kind="port", samples_cap=160):
     """Run the CPU oracle over a ScenarioBatch.  weights: [10] or [B,10].  Returns a dict of arrays."""
     B, N, R = batch.batch, batch.n_knots, batch.n_regions
+    # the sample buffer must hold every sample the path can produce (1 + 10 per segment): a buffer that is too small
+    # would be reported as the reference's CHECK failure by oracle_sample()
+    samples_cap = max(samples_cap, 10 * k_max + 8)
     w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
     stride = 0 if w.ndim == 1 else 1
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in batch.arrays()]

@@ -9,11 +9,17 @@ import helpers as H
 from spectral_b200 import api
 from spectral_b200.scenarios import GOLDEN_W_CUB, GOLDEN_W_TRP, WEIGHTS_FILE, config2, config3, load_fixture, perturbed_obstacles
 
-p = api.SpectralPlanner(device=0, max_batch=1024, n_max=128, r_max=8, k_max=32)
+p = api.SpectralPlanner(device=0, max_batch=1024, n_max=256, r_max=8, k_max=32)
 cases = [("cub", config2(1024, first=1024 * i), GOLDEN_W_CUB, "config2 shard %d" % i) for i in (1, 2, 3)]
 cases += [("trp", perturbed_obstacles(load_fixture("c1"), 512, seed=s), GOLDEN_W_TRP, "trp c1 seed %d" % s) for s in (101, 202)]
 cases += [("trp", config3(512, groups=g, first=4096), WEIGHTS_FILE, "config3 groups %d" % g) for g in (1, 64)]
 cases += [("cub", perturbed_obstacles(load_fixture("c3"), 512, seed=303), WEIGHTS_FILE, "cub c3 seed 303")]
+if os.environ.get("PARITY_SWEEP_MORE", "1") == "1":
+    from spectral_b200.scenarios import mixed_batches
+    cases += [(v, b, WEIGHTS_FILE, "mixed seed 777 #%d %s" % (i, v)) for i, (v, b) in enumerate(mixed_batches(1280, seed=777))]
+    for name in ("c7", "c5", "bounds", "c4"):
+        for v in ("trp", "cub"):
+            cases.append((v, perturbed_obstacles(load_fixture(name), 128, seed=404, s_max=100.0 if name == "c7" else 50.0), WEIGHTS_FILE, "%s %s seed 404" % (v, name)))
 bad = 0
 for variant, batch, w, name in cases:
     t = time.time()

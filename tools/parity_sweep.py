@@ -20,6 +20,13 @@ if os.environ.get("PARITY_SWEEP_MORE", "1") == "1":
     for name in ("c7", "c5", "bounds", "c4"):
         for v in ("trp", "cub"):
             cases.append((v, perturbed_obstacles(load_fixture(name), 128, seed=404, s_max=100.0 if name == "c7" else 50.0), WEIGHTS_FILE, "%s %s seed 404" % (v, name)))
+    rng = np.random.default_rng(9)
+    for Bodd in (1, 33, 1000):
+        cases.append(("cub", config2(Bodd, first=5000), GOLDEN_W_CUB, "config2 B=%d" % Bodd))
+    wr = np.tile(np.array(WEIGHTS_FILE), (256, 1))
+    wr[:, :4] = rng.uniform(0.5, 50.0, (256, 4)); wr[:, 4:8] = rng.uniform(0.0, 20.0, (256, 4)); wr[:, 8:] = rng.uniform(0.0, 40.0, (256, 2))
+    cases.append(("trp", perturbed_obstacles(load_fixture("c2"), 256, seed=505), wr, "trp c2 random weights"))
+    cases.append(("cub", config2(256, first=9000), wr, "cub config2 random weights"))
 bad = 0
 for variant, batch, w, name in cases:
     t = time.time()

@@ -53,6 +53,11 @@ extern "C" {
 #define SPECTRAL_FLAG_VERIFIED_S 4 /* s-axis control points satisfy the KKT conditions of the QP (exact optimum) */
 #define SPECTRAL_FLAG_VERIFIED_L 8 /* l-axis likewise */
 #define SPECTRAL_FLAG_VERIFIED (SPECTRAL_FLAG_VERIFIED_S | SPECTRAL_FLAG_VERIFIED_L)
+/* diagnostics of a polish that did not reach a KKT proof, four bits per axis (s: bits 4-7, l: bits 8-11):
+ * 1 stationarity / feasibility of the polished point not reached, 2 active set still changing after polish_rounds,
+ * 4 non-positive pivot in the polish factorisation, 8 polished point rejected (not better than the ADMM iterate) */
+#define SPECTRAL_FLAG_DIAG_SHIFT_S 4
+#define SPECTRAL_FLAG_DIAG_SHIFT_L 8
 
 #define SPECTRAL_FAIL_COST 100000000000.0 /* the reference's failure sentinel */
 
@@ -90,7 +95,8 @@ typedef struct {
   int weights_stride;      /* 1: one weight vector per scenario; 0: one for the whole batch */
 } SpectralInputs;
 
-/* Outputs; any pointer except K/status may be NULL to skip it. */
+/* Outputs.  Host-buffer entry points: any pointer except K/status may be NULL to skip it.  Device entry point
+ * (spectral_solve_batch_device): K, status, segs and ctrl are required (later stages read them), the rest optional. */
 typedef struct {
   int *K;             /* [B] segment count = new_corridor.size() */
   SpectralCube *segs; /* [B][k_max] the selected corridor sequence */

@@ -15,10 +15,11 @@
 #include "finalize.cuh"
 #include "qp.cuh"
 #include "qp_dense.cuh"
+#include "qp_anchor.cuh"
 #include "tables.cuh"
 
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
-extern "C" int spectral_corridor_prepare(int N, int R);                           // corridor.cu
+extern "C" int spectral_corridor_prepare(int N, int R, int *configured);                           // corridor.cu
 
 // ------------------------------------------------------------------ kernels
 __global__ void k_tables(const double *weights, double *mqm, int W) {
@@ -73,7 +74,10 @@ template <int LPA, int WPB>
 __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   extern __shared__ double qp_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  qp_warp_body<LPA, (LPA < 32 ? 2 * LPA : LPA)>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
+  // LPA = 32 (K > 16): the block's two warps are the s-axis and the l-axis problem of ONE scenario, solved jointly (JW = 64)
+  static_assert(LPA < 32 || WPB == 2, "a two-warp CTA per scenario");
+  qp_warp_body<LPA, 2 * LPA>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32,
+                             qp_smem + (size_t)WPB * QP_SM_DOUBLES_PER_LANE * 32);
 }
 
 // dense-operator ADMM kernel (qp_dense.cuh): one CTA (2 TA threads) per scenario of this class
@@ -84,6 +88,26 @@ template <int KC>
 __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, QPD_MINBLOCKS(KC)) k_qpd(const QpArgs a) {
   extern __shared__ __align__(16) double qpd_smem[];
   qpd_cta_body<KC>(a, blockIdx.x, threadIdx.x, qpd_smem, []() { __syncthreads(); });
+}
+
+// anchor-layout dense ADMM kernel (qp_anchor.cuh), KC <= 10.  Persistent: 2 CTAs per SM take scenarios of this class from
+// a device-side queue (a.next) until the list is drained -- no empty CTAs, no ragged last wave per launch.
+template <int KC>
+__global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a) {
+  extern __shared__ __align__(16) double qpd_smem[];
+  __shared__ int s_slot;
+  for (;;) {
+    if (threadIdx.x == 0) s_slot = atomicAdd(a.next, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    __syncthreads();
+    if (slot >= *a.count) return;
+    qpa_cta_body<KC>(a, slot, threadIdx.x, qpd_smem, []() { __syncthreads(); },
+                     [](int axis) {  // named barrier over the TA threads of one axis (ids as immediates: ptxas reserves only three)
+                       if (axis == 0) asm volatile("bar.sync 1, %0;" ::"n"(QpdLayout<KC>::TA) : "memory");
+                       else asm volatile("bar.sync 2, %0;" ::"n"(QpdLayout<KC>::TA) : "memory");
+                     });
+  }
 }
 
 // `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:
@@ -202,6 +226,8 @@ struct spectral_handle {
   double *d_ctrl = nullptr, *d_obj = nullptr, *d_cost = nullptr, *d_samples = nullptr, *d_lu = nullptr;
   size_t d_samples_bytes = 0, d_lu_bytes = 0;
   bool qp_attr_set = false;
+  int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
+  bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
 };
 
 static int fail(spectral_handle *h, int code, const std::string &msg) {
@@ -237,6 +263,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   }
   spectral_handle *h = new spectral_handle();
   h->device = device; h->max_batch = max_batch; h->n_max = n_max; h->r_max = r_max; h->k_max = k_max;
+  { const char *e = getenv("SPECTRAL_LEGACY_QPD"); h->legacy_qpd = e && e[0] == '1'; }
   *out = h;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -249,7 +276,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   const size_t B = (size_t)max_batch;
   CK(cudaMalloc(&h->cstatus, B * 4));
   CK(cudaMalloc(&h->lists, SP_NUM_CLASSES * B * 4));
-  CK(cudaMalloc(&h->counts, 4 * SP_NUM_CLASSES));
+  CK(cudaMalloc(&h->counts, 4 * 2 * SP_NUM_CLASSES));  // [0, NC): list lengths, [NC, 2 NC): queue heads of the persistent kernels
   CK(cudaMalloc(&h->axis_status, 2 * B * 4));
   CK(cudaMalloc(&h->axis_iters, 2 * B * 4));
   CK(cudaMalloc(&h->axis_polished, 2 * B * 4));
@@ -324,10 +351,21 @@ static cudaError_t launch_qpd(spectral_handle *h, const QpArgs &qa, int B, cudaS
   return cudaGetLastError();
 }
 
+template <int KC>
+static cudaError_t launch_qpa(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
+  const size_t smem = QpdLayout<KC>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(k_qpa<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+  k_qpa<KC><<<grid, 2 * QpdLayout<KC>::TA, smem, st>>>(qa);
+  h->launches++;
+  return cudaGetLastError();
+}
+
 template <int LPA, int WPB>
 static cudaError_t launch_qp(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
   constexpr int G = 32 / LPA;
-  const size_t smem = (size_t)WPB * QP_SMEM_PER_WARP;
+  const size_t smem = (size_t)WPB * QP_SMEM_PER_WARP + QP_XCH_DOUBLES * 8;
   cudaError_t e = cudaFuncSetAttribute(k_qp<LPA, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int warps = (2 * B + G - 1) / G;
@@ -362,14 +400,14 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
 
   // K1 + K2: corridors
   CorridorArgs ca{B, N, R, variant, h->k_max, delta_t, in->s_bounds, in->l_bounds, in->s_ref, in->l_ref, out->segs, out->K, h->cstatus};
-  if (spectral_corridor_prepare(N, R) != 0) return fail(h, SPECTRAL_ERR_CUDA, "corridor kernel: shared memory opt-in failed");
+  if (spectral_corridor_prepare(N, R, &h->corridor_smem) != 0) return fail(h, SPECTRAL_ERR_CUDA, "corridor kernel: shared memory opt-in failed");
   spectral_launch_corridor(ca, st);
   h->launches++;
   CK(cudaGetLastError());
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // classification by segment count -> lane class lists
-  CK(cudaMemsetAsync(h->counts, 0, 4 * SP_NUM_CLASSES, st));
+  CK(cudaMemsetAsync(h->counts, 0, 4 * 2 * SP_NUM_CLASSES, st));
   if (B <= 4096) k_classify_ordered<<<1, 1024, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   else k_classify<<<(B + 255) / 256, 256, 0, st>>>(h->cstatus, out->K, B, h->lists, h->counts);
   h->launches++;
@@ -395,9 +433,9 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
     if (cls > 0 && class_kcap(cls - 1) >= h->k_max) break;  // class cannot occur with this handle's k_max
     cudaStream_t cs = cls == 0 ? st : h->side[cls - 1];
     if (cls > 0) CK(cudaStreamWaitEvent(cs, h->ev_fork, 0));
-    qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls;
-    if (cls == 0) CK((launch_qpd<8>(h, qa, B, cs)));
-    else if (cls == 1) CK((launch_qpd<10>(h, qa, B, cs)));
+    qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls; qa.next = h->counts + SP_NUM_CLASSES + cls;
+    if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
+    else if (cls == 1) CK((h->legacy_qpd ? launch_qpd<10>(h, qa, B, cs) : launch_qpa<10>(h, qa, B, cs)));
     else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));
     else if (cls == 3) CK((launch_qpd<16>(h, qa, B, cs)));
     else CK((launch_qp<32, 2>(h, qa, B, cs)));
@@ -443,8 +481,11 @@ static int ensure(spectral_handle *h, T **p, size_t *cur, size_t need) {
 extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
                                           const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
   if (!h || !hin || !hout) return SPECTRAL_ERR_INVALID;
-  if (B <= 0 || B > h->max_batch) return fail(h, SPECTRAL_ERR_CAPACITY, "batch exceeds max_batch");
+  if (B <= 0 || B > h->max_batch || N < 3 || N > h->n_max || R < 1 || R > h->r_max)
+    return fail(h, SPECTRAL_ERR_CAPACITY, "batch shape exceeds the handle's capacity");
+  if (variant != SPECTRAL_TRP && variant != SPECTRAL_CUB) return fail(h, SPECTRAL_ERR_INVALID, "variant");
   if (!hout->K || !hout->status) return fail(h, SPECTRAL_ERR_INVALID, "K and status outputs are required");
+  if (hout->samples && hout->samples_cap <= 0) return fail(h, SPECTRAL_ERR_INVALID, "samples_cap");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t b = (size_t)B, n = (size_t)N, r = (size_t)R, km = (size_t)h->k_max;
@@ -460,17 +501,13 @@ extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int
   }
   {
     const size_t mb = (size_t)h->max_batch;
-    int rc = 0;
-    if (!h->d_K) rc |= dev_alloc(h, (void **)&h->d_K, mb * 4);
-    if (!h->d_status) rc |= dev_alloc(h, (void **)&h->d_status, mb * 4);
-    if (!h->d_iters) rc |= dev_alloc(h, (void **)&h->d_iters, mb * 4);
-    if (!h->d_flags) rc |= dev_alloc(h, (void **)&h->d_flags, mb * 4);
-    if (!h->d_npts) rc |= dev_alloc(h, (void **)&h->d_npts, mb * 4);
-    if (!h->d_segs) rc |= dev_alloc(h, (void **)&h->d_segs, mb * km * sizeof(SpectralCube));
-    if (!h->d_ctrl) rc |= dev_alloc(h, (void **)&h->d_ctrl, mb * 12 * km * 8);
-    if (!h->d_obj) rc |= dev_alloc(h, (void **)&h->d_obj, mb * 8);
-    if (!h->d_cost) rc |= dev_alloc(h, (void **)&h->d_cost, mb * 8);
-    if (rc) return SPECTRAL_ERR_CUDA;
+    int rc = SPECTRAL_SUCCESS;
+#define DEV_ALLOC(ptr, bytes) do { if (!(ptr) && rc == SPECTRAL_SUCCESS) rc = dev_alloc(h, (void **)&(ptr), (bytes)); } while (0)
+    DEV_ALLOC(h->d_K, mb * 4); DEV_ALLOC(h->d_status, mb * 4); DEV_ALLOC(h->d_iters, mb * 4); DEV_ALLOC(h->d_flags, mb * 4);
+    DEV_ALLOC(h->d_npts, mb * 4); DEV_ALLOC(h->d_segs, mb * km * sizeof(SpectralCube)); DEV_ALLOC(h->d_ctrl, mb * 12 * km * 8);
+    DEV_ALLOC(h->d_obj, mb * 8); DEV_ALLOC(h->d_cost, mb * 8);
+#undef DEV_ALLOC
+    if (rc) return rc;
   }
   if (hout->samples) { int rc = ensure(h, &h->d_samples, &h->d_samples_bytes, b * (size_t)hout->samples_cap * 48); if (rc) return rc; }
   if (hout->lu) { int rc = ensure(h, &h->d_lu, &h->d_lu_bytes, b * 2 * km * QP_ROWS * 16); if (rc) return rc; }

@@ -31,6 +31,8 @@ SP_DEV unsigned sp_ballot(int pred) { return __ballot_sync(SP_FULL, pred); }
 SP_DEV int sp_any(int pred) { return __any_sync(SP_FULL, pred); }
 SP_DEV int sp_all(int pred) { return __all_sync(SP_FULL, pred); }
 SP_DEV void sp_syncwarp() { __syncwarp(); }
+SP_DEV void sp_sync_cta() { __syncthreads(); }
+SP_DEV int sp_warp_in_cta() { return (int)(threadIdx.x >> 5); }
 SP_DEV int sp_popc(unsigned v) { return __popc(v); }
 SP_DEV int sp_ffs(unsigned v) { return __ffs(v); }
 // IEEE round-to-nearest without FMA contraction: the reference is x86-64 SSE2 code compiled

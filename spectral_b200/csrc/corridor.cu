@@ -11,12 +11,13 @@ __global__ void k_corridor(const CorridorArgs a) {
   corridor_cta_body(a, b, threadIdx.x >> 5, threadIdx.x & 31, corridor_smem, []() { __syncthreads(); });
 }
 
-extern "C" int spectral_corridor_prepare(int N, int R) {
+// cudaFuncSetAttribute applies to the CURRENT device: the caller (one handle per GPU) has set its device and remembers
+// the size it configured in *configured (per handle, so several handles / devices / threads in one process are fine).
+extern "C" int spectral_corridor_prepare(int N, int R, int *configured) {
   const CorridorSmem L = corridor_smem_layout(N, R);
-  static int configured = 0;
-  if (L.total > configured) {
+  if (L.total > *configured) {
     if (cudaFuncSetAttribute(k_corridor, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess) return -1;
-    configured = L.total;
+    *configured = L.total;
   }
   return 0;
 }

@@ -51,7 +51,8 @@ SP_DEV void finalize_body(const FinalArgs &a, int b) {
     iters = i0 > i1 ? i0 : i1;
     const int p0 = a.axis_polished[2 * b], p1 = a.axis_polished[2 * b + 1];
     flags = ((p0 & 1) ? SPECTRAL_FLAG_POLISHED_S : 0) | ((p1 & 1) ? SPECTRAL_FLAG_POLISHED_L : 0) |
-            ((p0 & 2) ? SPECTRAL_FLAG_VERIFIED_S : 0) | ((p1 & 2) ? SPECTRAL_FLAG_VERIFIED_L : 0);
+            ((p0 & 2) ? SPECTRAL_FLAG_VERIFIED_S : 0) | ((p1 & 2) ? SPECTRAL_FLAG_VERIFIED_L : 0) |
+            (((p0 >> 2) & 15) << SPECTRAL_FLAG_DIAG_SHIFT_S) | (((p1 >> 2) & 15) << SPECTRAL_FLAG_DIAG_SHIFT_L);
     obj = a.axis_obj[2 * b] + a.axis_obj[2 * b + 1];
   }
   double cost = SPECTRAL_FAIL_COST;

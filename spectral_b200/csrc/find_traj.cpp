@@ -18,6 +18,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,8 +30,14 @@
 
 namespace {
 const char *kDefaultDir = "/home/srujan_d/RISS/code/btrapz/src";
-spectral_handle_t *g_handle = nullptr;
-int g_nmax = 0, g_rmax = 0;
+// One lazily created handle per process, guarded by a mutex (the reference's find_traj is single-threaded and not
+// re-entrant w.r.t. its fixed file names either, trp_wrapper.cpp:23,288) and destroyed at unload.
+std::mutex g_mu;
+struct HandleOwner {
+  spectral_handle_t *h = nullptr;
+  int nmax = 0, rmax = 0;
+  ~HandleOwner() { if (h) spectral_destroy(h); }
+} g_own;
 
 std::string io_dir() {
   const char *d = getenv("SPECTRAL_IO_DIR");
@@ -41,6 +48,9 @@ bool verbose() { const char *v = getenv("SPECTRAL_VERBOSE"); return v && v[0] ==
 
 extern "C" double find_traj(SpectralParams *p) {
   const double kFail = SPECTRAL_FAIL_COST;
+  std::lock_guard<std::mutex> lock(g_mu);
+  spectral_handle_t *&g_handle = g_own.h;
+  int &g_nmax = g_own.nmax, &g_rmax = g_own.rmax;
   const std::string in_path = io_dir() + (SPECTRAL_VARIANT == SPECTRAL_TRP ? "/c_road_s1_2.txt" : "/c_road_s1_3.txt");
   std::ifstream ifs(in_path);
   if (!ifs.is_open()) {
@@ -56,8 +66,13 @@ extern "C" double find_traj(SpectralParams *p) {
   ifs >> R;                                             // :49
   ifs >> scalars[0] >> scalars[1];                      // ds_ref dl_ref :59
   for (int i = 2; i < 10; i++) ifs >> scalars[i];       // dd/ddd bounds :61-64
-  if (!ifs || N < 3 || N > 256 || R < 1 || R > 8) {
+  if (!ifs || N < 3 || R < 1) {
     std::cerr << "find_traj: malformed header in " << in_path << std::endl;
+    return kFail;
+  }
+  if (N > 256 || R > 8) {  // capacity of the corridor kernel's shared-memory slabs (SP_MAX_KNOTS / SP_MAX_REGIONS)
+    std::cerr << "find_traj: " << in_path << " has " << N << " knots / " << R << " regions; this build supports at most 256 / 8"
+              << std::endl;
     return kFail;
   }
   std::vector<double> sb((size_t)R * N * 2), lb((size_t)R * N * 2), dsb((size_t)N * 2), dlb((size_t)N * 2), sref(N), lref(N);
@@ -101,7 +116,13 @@ extern "C" double find_traj(SpectralParams *p) {
   SpectralOutputs out;
   out.K = &K; out.segs = segs.data(); out.ctrl = ctrl.data(); out.obj = &obj; out.a_cost = &a_cost; out.status = &status;
   out.iters = &iters; out.flags = &flags; out.npts = &npts; out.samples = samples.data(); out.samples_cap = cap; out.lu = nullptr;
-  if (spectral_solve_batch(g_handle, SPECTRAL_VARIANT, 1, N, R, delta_t, &in, nullptr, &out) != SPECTRAL_SUCCESS) {
+  // Options: the library defaults = the reference's OSQP settings (solve_3d.cc:1235-1243,1446-1462) plus the polish
+  // step, which returns the exact optimum of the QP instead of OSQP's eps = 1e-5 iterate (the reference sets polish = 0,
+  // :1243).  SPECTRAL_POLISH=0 switches it off: the output is then the raw ADMM iterate like the reference's.
+  SpectralOptions opt;
+  spectral_default_options(&opt);
+  if (const char *pol = getenv("SPECTRAL_POLISH")) opt.polish = pol[0] != '0';
+  if (spectral_solve_batch(g_handle, SPECTRAL_VARIANT, 1, N, R, delta_t, &in, &opt, &out) != SPECTRAL_SUCCESS) {
     std::cerr << "find_traj: " << spectral_last_error(g_handle) << std::endl;
     return kFail;
   }

@@ -34,6 +34,8 @@
 #define QP_SM_DOUBLES_PER_LANE 105
 #define QP_SMEM_PER_WARP (QP_SM_DOUBLES_PER_LANE * 32 * 8)
 
+#define QP_XCH_DOUBLES 4                        // cross-warp exchange scratch of a two-warp joint instance (JW = 64)
+
 #define LT(i, j) ((i) * ((i) + 1) / 2 + (j))  // packed lower triangle, i >= j
 
 #define QP_RUNNING 0
@@ -52,6 +54,7 @@ struct QpArgs {
   const int *K;
   const int *list;   // scenario ids of this lane-class
   const int *count;  // number of entries in list
+  int *next;         // persistent kernels: next list entry to take (device counter, zeroed with the counts)
   SpOptionsDev opt;
   double *ctrl;      // [B][12*k_max]
   int *axis_status;  // [B][2]
@@ -146,6 +149,39 @@ SP_DEV void apply_P(const double *sm, int lane, const double x[6], double y[6]) 
       y[i] += p * x[j];
       if (i != j) y[j] += p * x[i];
     }
+}
+
+// ------------------------------------------------------------------ joint reductions
+// Reductions over the JW lanes that form ONE OSQP instance (the s-axis and the l-axis problem of a scenario, solved jointly
+// like the reference does).  JW <= 32: adjacent lane groups of one warp.  JW = 64 (LPA = 32, K > 16): the two axis problems
+// sit in the two WARPS of one CTA and meet through `xch` (QP_XCH_DOUBLES of shared memory) and the CTA barrier; both
+// warps take every joint decision from the same reduced values, so they reach every barrier together.
+template <int JW>
+SP_DEV double qp_joint_max(double v, double *xch) {
+  if (JW <= 32) return sp_group_max(v, JW);
+  v = sp_group_max(v, 32);
+  const int w = sp_warp_in_cta() & 1;
+  xch[w] = v;  // (every lane writes the same value)
+  sp_sync_cta();
+  const double r = fmax(xch[0], xch[1]);
+  sp_sync_cta();
+  return r;
+}
+template <int JW>
+SP_DEV double qp_joint_sum(double v, double *xch) {
+  if (JW <= 32) return sp_group_sum(v, JW);
+  v = sp_group_sum(v, 32);
+  const int w = sp_warp_in_cta() & 1;
+  xch[w] = v;
+  sp_sync_cta();
+  const double r = xch[0] + xch[1];
+  sp_sync_cta();
+  return r;
+}
+template <int JW>
+SP_DEV int qp_joint_or(int v, double *xch) {
+  if (JW <= 32) return sp_group_or(v, JW);
+  return qp_joint_max<JW>(sp_group_or(v, 32) ? 1.0 : 0.0, xch) != 0.0 ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ factorisation of S
@@ -373,7 +409,7 @@ struct QpResid {
 template <int LPA, int STR, int RW>
 SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const double q[6], const double cD[6],
                             double c_over_rhobar, unsigned eqmask, double t, double tp, double tn, bool first, bool last,
-                            bool active) {
+                            bool active, double *xch = nullptr) {
   double Ax[QP_ROWS], y[QP_ROWS];
   {
     double p3 = sp_shfl_up(x[3], 1, LPA), p4 = sp_shfl_up(x[4], 1, LPA), p5 = sp_shfl_up(x[5], 1, LPA);
@@ -409,9 +445,9 @@ SP_DEV QpResid qp_residuals(const double *sm, int lane, const double x[6], const
   }
   QpResid R;
   if (!active) { pri = 0; dua = 0; nz = 0; nax = 0; nq = 0; npx = 0; naty = 0; }
-  R.pri = sp_group_max(pri, RW); R.dua = sp_group_max(dua, RW); R.nz = sp_group_max(nz, RW);
-  R.nax = sp_group_max(nax, RW); R.nq = sp_group_max(nq, RW); R.npx = sp_group_max(npx, RW);
-  R.naty = sp_group_max(naty, RW);
+  R.pri = qp_joint_max<RW>(pri, xch); R.dua = qp_joint_max<RW>(dua, xch); R.nz = qp_joint_max<RW>(nz, xch);
+  R.nax = qp_joint_max<RW>(nax, xch); R.nq = qp_joint_max<RW>(nq, xch); R.npx = qp_joint_max<RW>(npx, xch);
+  R.naty = qp_joint_max<RW>(naty, xch);
   return R;
 }
 
@@ -427,13 +463,14 @@ struct QpLane {
   double q[6], sig[6], cD[6];
   double c, rhobar;
   unsigned eqmask;
+  double *xch;  // cross-warp exchange scratch (JW = 64 only)
   int pre;  // interval pre-check: the scenario's corridor is provably empty (SpectralOptions::infeasibility_precheck)
 };
 
 // K3 + Ruiz equilibration + per-row rho: fills the shared-memory slots L, U, W (= 0), P, RHO of this
 // lane and the lane state.  `lane` is the shared-memory column of this lane (slot * STR + lane).
 template <int LPA, int STR, int JW>
-SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, double *sm, QpLane &Q) {
+SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, double *sm, QpLane &Q, double *xch = nullptr) {
   const int b = have ? a.list[ap >> 1] : 0;
   const int axis = ap & 1;
   const int K = have ? a.K[b] : 0;
@@ -549,7 +586,7 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
       bad = bad || (lo[19] > hi[6] + mg) || (lo[19] < lo[6] - mg);
       bad = bad || (lo[20] > hi[11] + mg) || (lo[20] < lo[11] - mg);
     }
-    pre = sp_group_or(bad ? 1 : 0, JW);
+    pre = qp_joint_or<JW>(bad ? 1 : 0, xch);
   }
   if (a.lu != nullptr && active) {
     double *dst = a.lu + (((size_t)b * 2 + axis) * a.k_max + seg) * QP_ROWS * 2;
@@ -672,8 +709,8 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
       qn = fmax(qn, c * D[j] * fabs(q[j]));
     }
     if (!active) { colsum = 0.0; qn = 0.0; }
-    colsum = sp_group_sum(colsum, JW);
-    qn = sp_group_max(qn, JW);
+    colsum = qp_joint_sum<JW>(colsum, xch);
+    qn = qp_joint_max<JW>(qn, xch);
     double ct = colsum / (nvars > 0 ? nvars : 1.0);
     qn = limit_scaling(qn);
     ct = ct > qn ? ct : qn;
@@ -696,7 +733,7 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
 
   Q.b = b; Q.axis = axis; Q.K = K; Q.seg = seg; Q.kmaxw = kmaxw;
   Q.have = have; Q.active = active; Q.first = first; Q.last = last;
-  Q.t = t; Q.tp = tp; Q.tn = tn; Q.c = c; Q.rhobar = rhobar; Q.eqmask = eqmask; Q.pre = pre;
+  Q.t = t; Q.tp = tp; Q.tn = tn; Q.c = c; Q.rhobar = rhobar; Q.eqmask = eqmask; Q.pre = pre; Q.xch = xch;
 #pragma unroll
   for (int j = 0; j < 6; j++) { Q.q[j] = q[j]; Q.sig[j] = sig[j]; Q.cD[j] = cD[j]; }
 }
@@ -719,7 +756,7 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
   QP_UNPACK_LANE(Q);
   double rhobar = Q.rhobar;
   int bad = qp_factorize<LPA, STR>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
-  bad = sp_group_or(bad, JW);
+  bad = qp_joint_or<JW>(bad, Q.xch);
 
   // ---------------- ADMM (OSQP iteration in w form) ----------------
 #pragma unroll
@@ -781,7 +818,7 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
     }
     if (run) iters = it;
     if (check) {
-      QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
+      QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active, Q.xch);
       const double eps_p = o.eps_abs + o.eps_rel * fmax(R.nz, R.nax);
       const double eps_d = o.eps_abs + o.eps_rel * fmax(R.nq, fmax(R.npx, R.naty));
       int newstate = QP_RUNNING;
@@ -793,8 +830,8 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
 #pragma unroll
           for (int r = 0; r < QP_ROWS; r++) v[r] = 0.0;
         }
-        const double nd = sp_group_max(dy_norm, JW);
-        const double lhs = sp_group_sum(dy_lhs, JW);
+        const double nd = qp_joint_max<JW>(dy_norm, Q.xch);
+        const double lhs = qp_joint_sum<JW>(dy_lhs, Q.xch);
         double atd[6];
         double n18 = sp_shfl_down(v[18], 1, LPA), n19 = sp_shfl_down(v[19], 1, LPA), n20 = sp_shfl_down(v[20], 1, LPA);
         if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
@@ -803,7 +840,7 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
 #pragma unroll
         for (int j = 0; j < 6; j++) na = fmax(na, fabs(cD[j] * atd[j]));
         if (!active || !run) na = 0.0;
-        na = sp_group_max(na, JW);
+        na = qp_joint_max<JW>(na, Q.xch);
         if (R.pri < eps_p && R.dua < eps_d) newstate = QP_ST_SOLVED;
         else if (!(R.pri < eps_p) && nd > o.eps_pinf && lhs < -o.eps_pinf * nd && na < o.eps_pinf * nd)
           newstate = QP_ST_INFEASIBLE;
@@ -831,7 +868,7 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
           }
           sp_syncwarp();
           int b2 = qp_factorize<LPA, STR>(sm, lane, QP_SM_RHO, sig, t, tp, tn, first, last, active, seg, kmaxw, 0u, eqmask, 0.0, F);
-          b2 = sp_group_or(b2, JW);
+          b2 = qp_joint_or<JW>(b2, Q.xch);
           if (b2 && state == QP_RUNNING) state = QP_ST_INFEASIBLE;
         }
       }
@@ -857,7 +894,7 @@ SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x
   const SpOptionsDev &o = a.opt;
   const double rhobar = Q.rhobar;
   if (JW != LPA) {
-    QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active);
+    QpResid R = qp_residuals<LPA, STR, JW>(sm, lane, x, q, cD, c / rhobar, eqmask, t, tp, tn, first, last, active, Q.xch);
     if (state == QP_RUNNING) state = qp_maxiter_state(o, R);
   }
   // per-axis residuals of the ADMM iterate: the yardstick of the polish acceptance below
@@ -895,7 +932,7 @@ SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x
 #pragma unroll
     for (int j = 0; j < 6; j++) sigp[j] = sig[j] * (1e-12 / o.sigma);
     double xp[6];
-    int verified = 0, badp = 0;
+    int verified = 0, badp = 0, last_changed = 0;
     double prip = 0.0, duap = 0.0;
     const int rounds = o.polish_rounds > 0 ? o.polish_rounds : 1;
     for (int round = 0; round < rounds; round++) {
@@ -1012,6 +1049,7 @@ SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x
                                    b, axis, round, sp_popc(actm), prip, duap, tol_p, tol_d, changed, verified, last_res.pri, last_res.dua);
 #endif
       if (!changed && !badp && !verified) verified = 1;
+      last_changed = changed;
       if (sp_all(verified || !solved || badp || changed == 2)) break;
     }
     // acceptance (OSQP polish.c): polished residuals must beat the ADMM ones, in the scaled space
@@ -1023,6 +1061,10 @@ SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x
 #pragma unroll
       for (int j = 0; j < 6; j++) x[j] = xp[j];
     }
+    // diagnostics of a polish that proved nothing (flags bits 4.., include/spectral.h): why
+    if (solved && !verified)
+      polished |= badp ? 16 : ((last_changed & 2) ? 4 : 8);   // bad pivot | stationarity / feasibility not reached | active set still changing
+    if (solved && !(polished & 1)) polished |= 32;            // polished point rejected (not better than the ADMM iterate)
   }
 
   // ---------------- outputs ----------------
@@ -1050,7 +1092,7 @@ SP_DEV void qp_finish(const QpArgs &a, double *sm, int lane, QpLane &Q, double x
 
 // One warp = 32/LPA axis problems (k_qp): setup, lane-per-segment ADMM, finish.
 template <int LPA, int JW>
-SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm) {
+SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm, double *xch) {
   constexpr int G = 32 / LPA;
   const int cnt = *a.count;
   const int grp = lane / LPA, seg = lane % LPA;
@@ -1058,7 +1100,7 @@ SP_DEV void qp_warp_body(const QpArgs &a, int warp_global, int lane, double *sm)
   if (warp_global * G >= 2 * cnt) return;
   const bool have = ap < 2 * cnt;
   QpLane Q;
-  qp_setup<LPA, 32, JW>(a, ap, have, seg, lane, sm, Q);
+  qp_setup<LPA, 32, JW>(a, ap, have, seg, lane, sm, Q, xch);
   QpFactor F;
   double x[6];
   int state, iters;

@@ -376,7 +376,7 @@ SP_DEV void qpd_load_lane(QpLane &Q, const QpArgs &a, int ap, int seg, const dou
   Q.t = d[0]; Q.tp = d[1]; Q.tn = d[2];
 #pragma unroll
   for (int j = 0; j < 6; j++) { Q.q[j] = d[3 + j]; Q.sig[j] = d[9 + j]; Q.cD[j] = d[15 + j]; }
-  Q.c = c; Q.rhobar = rhobar; Q.eqmask = (unsigned)eq[seg]; Q.pre = 0;
+  Q.c = c; Q.rhobar = rhobar; Q.eqmask = (unsigned)eq[seg]; Q.pre = 0; Q.xch = nullptr;
 }
 
 // warp 0: K3 assembly, Ruiz scaling, per-row rho, stencil tables, first factorisation.

@@ -160,3 +160,20 @@ def mixed_batches(B: int, seed: int = 20230602, bases: Sequence[str] = ("c1", "c
             b = perturbed_obstacles(load_fixture(name), per, seed=seed + 17 * i + (variant == "cub"))
             out.append((variant, with_extra_breaks(b, seed + 1000 + i)))
     return out
+
+
+def zigzag_breaks(base: Scenario, B: int, seed: int = 4242, s_max: float = 100.0) -> ScenarioBatch:
+    """Scenarios with MANY segments (K up to ~30, the class above the dense kernels' capacity): the config-2 perturbation of
+    `base` plus a staircase in the upper s-bound of every region (a 0.3 .. 0.6 m step every p in {5 .. 9} knots), each
+    step being a slope break of CorridorGeneration (solve_3d.cc:372-374)."""
+    batch = perturbed_obstacles(base, B, seed=seed, s_max=s_max)
+    rng = np.random.Generator(np.random.Philox(key=seed + 1))
+    N = batch.n_knots
+    period = rng.integers(5, 10, size=B)
+    step = np.round(0.3 + 0.3 * rng.random(B), 2)
+    knots = np.arange(N)[None, :]
+    stair = ((knots // period[:, None]) % 2) * step[:, None]          # [B, N]
+    s = batch.s_bounds.copy()
+    s[:, :, :, 1] = np.maximum(s[:, :, :, 1] - stair[:, None, :], s[:, :, :, 0])
+    return ScenarioBatch(N, batch.n_regions, batch.delta_t, s, batch.l_bounds, batch.ds_bounds, batch.dl_bounds, batch.s_ref,
+                         batch.l_ref, batch.init, batch.scalars)

@@ -117,12 +117,21 @@ def test_find_traj_failure_sentinel(tmp_path):
 
 
 # ---------------------------------------------------------------- batches vs the oracle
+NO_POLISH = dict(polish=0)  # the reference's own setting (solve_3d.cc:1243): the output is the raw ADMM iterate
+
+
+def _raw(planner, variant, batch, weights):
+    """The product run with the reference's polish = 0: its ADMM iterate, compared with the reference-settings oracle's."""
+    return planner.solve(variant, batch, weights, options=api.default_options(**NO_POLISH))
+
+
 def test_config2_cub_1024_vs_oracle(planner):
     """BASELINE configs[1]: 1024 obstacle-perturbed copies of scenario_1, cuboid variant."""
     batch = config2(1024)
     got = planner.solve("cub", batch, GOLDEN_W_CUB, samples_cap=160)
     ref, ref0 = H.oracle_pair("cub", batch, GOLDEN_W_CUB)
-    both = H.assert_batch_parity(got, ref, "config2", need_verified_frac=0.6, ref0=ref0, batch=batch, variant="cub", weights=GOLDEN_W_CUB)
+    both = H.assert_batch_parity(got, ref, "config2", need_verified_frac=0.6, ref0=ref0, batch=batch, variant="cub", weights=GOLDEN_W_CUB,
+                                 got0=_raw(planner, "cub", batch, GOLDEN_W_CUB))
     for b in np.nonzero(both)[0][:64]:
         n = int(got.npts[b])
         assert H.close(got.samples[b, :n], ref["samples"][b, :n], rtol=1e-5, atol=2e-6)
@@ -132,7 +141,8 @@ def test_config2_trp_512_vs_oracle(planner):
     batch = perturbed_obstacles(load_fixture("c1"), 512, seed=77)
     got = planner.solve("trp", batch, GOLDEN_W_TRP)
     ref, ref0 = H.oracle_pair("trp", batch, GOLDEN_W_TRP)
-    H.assert_batch_parity(got, ref, "trp512", need_verified_frac=0.6, ref0=ref0, batch=batch, variant="trp", weights=GOLDEN_W_TRP)
+    H.assert_batch_parity(got, ref, "trp512", need_verified_frac=0.6, ref0=ref0, batch=batch, variant="trp", weights=GOLDEN_W_TRP,
+                          got0=_raw(planner, "trp", batch, GOLDEN_W_TRP))
 
 
 def test_config3_shared_structure_groups_vs_oracle(planner):
@@ -140,7 +150,8 @@ def test_config3_shared_structure_groups_vs_oracle(planner):
     batch = config3(512, groups=8)
     got = planner.solve("trp", batch, WEIGHTS_FILE)
     ref, ref0 = H.oracle_pair("trp", batch, WEIGHTS_FILE)
-    H.assert_batch_parity(got, ref, "config3", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="trp", weights=WEIGHTS_FILE)
+    H.assert_batch_parity(got, ref, "config3", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="trp", weights=WEIGHTS_FILE,
+                          got0=_raw(planner, "trp", batch, WEIGHTS_FILE))
     for g in range(8):  # one structure per group, as the generator promises
         m = np.arange(512) % 8 == g
         assert len(set(got.K[m])) == 1
@@ -151,7 +162,8 @@ def test_mixed_variable_structure_vs_oracle(planner):
     for variant, batch in mixed_batches(640, seed=20230602):
         got = planner.solve(variant, batch, WEIGHTS_FILE)
         ref, ref0 = H.oracle_pair(variant, batch, WEIGHTS_FILE)
-        H.assert_batch_parity(got, ref, "mixed/%s" % variant, need_verified_frac=0.5, ref0=ref0, batch=batch, variant=variant, weights=WEIGHTS_FILE)
+        H.assert_batch_parity(got, ref, "mixed/%s" % variant, need_verified_frac=0.5, ref0=ref0, batch=batch, variant=variant, weights=WEIGHTS_FILE,
+                              got0=_raw(planner, variant, batch, WEIGHTS_FILE))
 
 
 def test_per_scenario_weights(planner):
@@ -162,7 +174,21 @@ def test_per_scenario_weights(planner):
     w[:, 5] = rng.uniform(1.0, 50.0, 256)
     got = planner.solve("cub", batch, w)
     ref, ref0 = H.oracle_pair("cub", batch, w)
-    H.assert_batch_parity(got, ref, "weights", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="cub", weights=w)
+    H.assert_batch_parity(got, ref, "weights", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="cub", weights=w,
+                          got0=_raw(planner, "cub", batch, w))
+
+
+def test_many_segments_class_vs_oracle(planner):
+    """K > 16 (the lane-per-segment kernel k_qp<32,2>, above the dense kernels' capacity): the N = 121 fixture with
+    a staircase in the s-bounds gives K in [11, 29], 39 of 64 scenarios above 16.  Same bars as everywhere: segments bit-exact, the two axes solved as ONE
+    OSQP instance (iteration count = the reference-settings oracle's), iterate and optimum parity."""
+    from spectral_b200.scenarios import zigzag_breaks
+    batch = zigzag_breaks(load_fixture("c7"), 64)
+    got = planner.solve("trp", batch, WEIGHTS_FILE)
+    assert (got.K > 16).sum() >= 30, got.K
+    ref, ref0 = H.oracle_pair("trp", batch, WEIGHTS_FILE)
+    H.assert_batch_parity(got, ref, "K>16", ref0=ref0, batch=batch, variant="trp", weights=WEIGHTS_FILE,
+                          got0=_raw(planner, "trp", batch, WEIGHTS_FILE), max_undecided_mismatch_frac=0.05)
 
 
 def test_edge_cases(planner):

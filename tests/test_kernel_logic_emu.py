@@ -50,9 +50,8 @@ def test_emu_full_solve_c2_matches_converged_oracle():
     assert both.all()
     n = int(got.npts[0])
     assert H.close(got.samples[0, :n], ref["samples"][0, :n], rtol=1e-5, atol=2e-6)
-    # iteration counts are not a parity quantity: the kernel solves the s and l axes as two OSQP instances
-    # (the QP is block diagonal), the reference solves them jointly with one rho / one cost scaling
-    assert 0 < int(got.iters[0]) < 5000 and int(ref0["iters"][0]) < 5000
+    # both axes are solved as ONE OSQP instance like the reference's single osqp_solve: same iteration count
+    assert int(got.iters[0]) == int(ref0["iters"][0]) < 5000
 
 
 def _subset(batch, idx):
@@ -74,6 +73,32 @@ def test_emu_dense_kernel_tracks_reference_osqp():
     assert np.array_equal(got.iters, ref0["iters"]), (got.iters, ref0["iters"])
     assert np.array_equal(got.ok(), ref0["status"] <= 1)
     H.assert_batch_parity(got, ref, "emu/dense", need_verified_frac=1.0, ref0=ref0)
+
+
+def test_emu_anchor_layout_equals_fullrow(monkeypatch):
+    """The anchor layout (qp_anchor.cuh, the K <= 10 classes) orders the arithmetic of every iterate exactly like the
+    full-row loop of qp_dense.cuh it replaces: identical control points, iteration counts and flags, bit for bit
+    (K = 9 -> k_qpa<10>, an early infeasible K = 4 -> k_qpa<8>, adaptive-rho updates on the way)."""
+    from spectral_b200.scenarios import GOLDEN_W_CUB
+    batch = _subset(config2(1024), [779, 914])
+    new = H.emu_solve("cub", batch, GOLDEN_W_CUB)
+    monkeypatch.setenv("SPECTRAL_LEGACY_QPD", "1")
+    old = H.emu_solve("cub", batch, GOLDEN_W_CUB)
+    assert list(new.K) == [9, 4]
+    assert np.array_equal(new.iters, old.iters) and np.array_equal(new.status, old.status) and np.array_equal(new.flags, old.flags)
+    assert np.array_equal(new.ctrl, old.ctrl) and np.array_equal(new.obj, old.obj)
+
+
+def test_emu_many_segments_joint_solve():
+    """K > 16 (k_qp<32,2>: one warp per axis, joint reductions across the two warps): the iteration count equals the
+    reference-settings oracle's, i.e. the two axes really are ONE OSQP instance (they were two)."""
+    from spectral_b200.scenarios import zigzag_breaks
+    batch = _subset(zigzag_breaks(load_fixture("c7"), 64), [8, 16])   # K = 18 (certified infeasible), K = 19 (solved)
+    got = H.emu_solve("trp", batch, WEIGHTS_FILE, polish=0)
+    ref0 = po.solve_batch("trp", batch, WEIGHTS_FILE, mode=0)
+    assert list(got.K) == [18, 19]
+    assert np.array_equal(got.iters, ref0["iters"]) and np.array_equal(got.ok(), ref0["status"] <= 1)
+    assert H.maxdiff(got.ctrl[1, :12 * 19], ref0["ctrl"][1, :12 * 19]) < 1e-5
 
 
 def test_emu_lane_kernel_matches_dense_kernel(monkeypatch):

@@ -8,6 +8,7 @@
 #include "../../spectral_b200/csrc/corridor.cuh"
 #include "../../spectral_b200/csrc/qp.cuh"
 #include "../../spectral_b200/csrc/qp_dense.cuh"
+#include "../../spectral_b200/csrc/qp_anchor.cuh"
 #include "../../spectral_b200/csrc/tables.cuh"
 #include "../../spectral_b200/csrc/finalize.cuh"
 
@@ -18,6 +19,8 @@
 
 thread_local EmuWarp *emu_warp = nullptr;
 thread_local int emu_lane = 0;
+thread_local pthread_barrier_t *emu_cta = nullptr;
+thread_local int emu_warp_id = 0;
 
 static void run_warps(int nwarps, const std::function<void(int, int, pthread_barrier_t *)> &fn) {
   std::vector<EmuWarp> warps(nwarps);
@@ -30,6 +33,8 @@ static void run_warps(int nwarps, const std::function<void(int, int, pthread_bar
       th.emplace_back([&, w, l]() {
         emu_warp = &warps[w];
         emu_lane = l;
+        emu_cta = &cta;
+        emu_warp_id = w;
         fn(w, l, &cta);
       });
   for (auto &t : th) t.join();
@@ -45,6 +50,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
                                double *obj, double *a_cost, int *status, int *iters, int *flags, int *npts,
                                double *samples, int samples_cap, double *lu) {
   const bool force_lanes = getenv("SPECTRAL_EMU_LANES") != nullptr;  // run the lane-per-segment loop for every class
+  const bool legacy_qpd = getenv("SPECTRAL_LEGACY_QPD") != nullptr;   // the full-row loop instead of the anchor layout (K <= 10)
   std::vector<int> cstatus(B, 0);
   // ---- corridor kernel: one CTA per scenario, R warps
   CorridorArgs ca{B, N, R, variant, k_max, delta, s_bounds, l_bounds, s_ref, l_ref, segs, K, cstatus.data()};
@@ -84,7 +90,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
     qa.N = N; qa.k_max = k_max; qa.variant = variant; qa.delta = delta;
     qa.ds_bounds = ds_bounds; qa.dl_bounds = dl_bounds; qa.s_ref = s_ref; qa.l_ref = l_ref; qa.init = init;
     qa.scalars = scalars; qa.weights = weights; qa.wstride = wstride; qa.mqm = mqm.data(); qa.segs = segs; qa.K = K;
-    qa.list = list[cls].data(); qa.count = &cnt; qa.opt = od; qa.ctrl = ctrl; qa.axis_status = axis_status.data();
+    qa.list = list[cls].data(); qa.count = &cnt; qa.next = nullptr; qa.opt = od; qa.ctrl = ctrl; qa.axis_status = axis_status.data();
     qa.axis_iters = axis_iters.data(); qa.axis_polished = axis_pol.data(); qa.axis_obj = axis_obj.data(); qa.lu = lu;
     if (cls <= 3 && !force_lanes) {
       // dense kernel: one CTA of 2 TA threads per scenario
@@ -94,25 +100,40 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
         std::vector<double> sm(total + 2);
         double *base = sm.data();
         if ((uintptr_t)base & 15) base += 1;
+        pthread_barrier_t axbar[2];
+        for (auto &ab : axbar) pthread_barrier_init(&ab, nullptr, 32 * nwarps / 2);
         run_warps(nwarps, [&](int w, int l, pthread_barrier_t *cta) {
           auto sync = [cta]() { pthread_barrier_wait(cta); };
-          if (cls == 0) qpd_cta_body<8>(qa, slot, 32 * w + l, base, sync);
+          auto sync_axis = [&axbar](int axis) { pthread_barrier_wait(&axbar[axis]); };
+          if (cls == 0 && !legacy_qpd) qpa_cta_body<8>(qa, slot, 32 * w + l, base, sync, sync_axis);
+          else if (cls == 1 && !legacy_qpd) qpa_cta_body<10>(qa, slot, 32 * w + l, base, sync, sync_axis);
+          else if (cls == 0) qpd_cta_body<8>(qa, slot, 32 * w + l, base, sync);
           else if (cls == 1) qpd_cta_body<10>(qa, slot, 32 * w + l, base, sync);
           else if (cls == 2) qpd_cta_body<12>(qa, slot, 32 * w + l, base, sync);
           else qpd_cta_body<16>(qa, slot, 32 * w + l, base, sync);
         });
+        for (auto &ab : axbar) pthread_barrier_destroy(&ab);
       }
       continue;
     }
     const int lpa = cls <= 0 ? 8 : (cls <= 3 ? 16 : 32);
+    if (lpa == 32) {  // k_qp<32, 2>: one CTA of two warps per scenario (s-axis warp, l-axis warp, joint reductions)
+      for (int slot = 0; slot < cnt; slot++) {
+        std::vector<double> sm(2 * QP_SM_DOUBLES_PER_LANE * 32 + QP_XCH_DOUBLES);
+        run_warps(2, [&](int w, int l, pthread_barrier_t *) {
+          qp_warp_body<32, 64>(qa, 2 * slot + w, l, sm.data() + (size_t)w * QP_SM_DOUBLES_PER_LANE * 32,
+                               sm.data() + 2 * QP_SM_DOUBLES_PER_LANE * 32);
+        });
+      }
+      continue;
+    }
     const int G = 32 / lpa;
     const int nw = (2 * cnt + G - 1) / G;
     for (int w = 0; w < nw; w++) {
       std::vector<double> sm(QP_SM_DOUBLES_PER_LANE * 32);
       run_warps(1, [&](int, int l, pthread_barrier_t *) {
-        if (lpa == 8) qp_warp_body<8, 16>(qa, w, l, sm.data());
-        else if (lpa == 16) qp_warp_body<16, 32>(qa, w, l, sm.data());
-        else qp_warp_body<32, 32>(qa, w, l, sm.data());
+        if (lpa == 8) qp_warp_body<8, 16>(qa, w, l, sm.data(), nullptr);
+        else qp_warp_body<16, 32>(qa, w, l, sm.data(), nullptr);
       });
     }
   }

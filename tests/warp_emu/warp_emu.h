@@ -23,6 +23,8 @@ struct EmuWarp {
 };
 extern thread_local EmuWarp *emu_warp;
 extern thread_local int emu_lane;
+extern thread_local pthread_barrier_t *emu_cta;  // the CTA barrier of the running emulated block
+extern thread_local int emu_warp_id;
 
 inline void emu_sync() { pthread_barrier_wait(&emu_warp->bar); }
 
@@ -67,6 +69,8 @@ inline unsigned sp_ballot(int pred) {
 inline int sp_any(int pred) { return sp_ballot(pred) != 0; }
 inline int sp_all(int pred) { return sp_ballot(pred) == 0xffffffffu; }
 inline void sp_syncwarp() { emu_sync(); }
+inline void sp_sync_cta() { pthread_barrier_wait(emu_cta); }
+inline int sp_warp_in_cta() { return emu_warp_id; }
 inline int sp_popc(unsigned v) { return __builtin_popcount(v); }
 inline int sp_ffs(unsigned v) { return __builtin_ffs((int)v); }
 // compiled with -ffp-contract=off, so plain operators are IEEE round-to-nearest without FMA

@@ -193,10 +193,20 @@ int spectral_measure_fp64_peak(spectral_handle_t *h, double *tflops);
 int spectral_set_timing(spectral_handle_t *h, int enabled);
 int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_KERNELS], int *calls);
 
+/* The solver classes by segment count K (one kernel each, forked streams): K <= 8, <= 10, <= 12, <= 16, <= 32.
+ * spectral_get_class_timing: summed device ms of each class' kernel (events on that class' stream) over the calls recorded
+ * since spectral_set_timing(h, 1); classes overlap in time, so the entries do not add up to the "qp" stage time. */
+#define SPECTRAL_NUM_CLASSES 5
+int spectral_get_class_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_CLASSES]);
+
 /* Work counters accumulated on the device by every solve_batch*_ call (synchronises the device):
- * work[0] ADMM iterations summed over axis problems, work[1] their algorithmic flops
- * (72 K^2 + 208 K - 24 per axis-iteration: dense apply of the 6K x 6K inverse + A, A' products), work[2] scenarios processed, work[3] scenarios solved. */
-int spectral_get_work(spectral_handle_t *h, double work[4], int reset);
+ * work[0] ADMM iterations summed over axis problems; work[1] their flops in the dense-operator count the kernels execute
+ * (72 K^2 + 208 K - 24 per axis-iteration: dense apply of the 6K x 6K inverse + A, A' products); work[2] scenarios
+ * processed; work[3] scenarios solved; work[4] sum of K (segments written by the corridor kernel); work[5] the iterations
+ * in the variable-structure count of SURVEY.md 8d (424 K - 168 per axis-iteration: block-tridiagonal solve, the algorithmic
+ * minimum without a shared KKT matrix); work[6 + c] the dense-count flops of solver class c; the rest reserved. */
+#define SPECTRAL_NUM_WORK 12
+int spectral_get_work(spectral_handle_t *h, double work[SPECTRAL_NUM_WORK], int reset);
 
 /* The reference's plugin entry point (exported by libtrp.so / libcub.so, not by libspectral.so):
  *   double find_traj(SpectralParams *p);                       trp_wrapper.cpp:20, cub_wrapper.cpp:19 */

@@ -32,6 +32,8 @@ FLAG_POLISHED_S, FLAG_POLISHED_L, FLAG_VERIFIED_S, FLAG_VERIFIED_L = 1, 2, 4, 8
 FLAG_VERIFIED = FLAG_VERIFIED_S | FLAG_VERIFIED_L
 FAIL_COST = 100000000000.0
 NUM_KERNELS = 6
+NUM_CLASSES = 5
+NUM_WORK = 12
 KERNEL_NAMES = ("tables", "corridor", "classify", "qp", "finalize", "argmin")
 
 CUBE_DTYPE = np.dtype([
@@ -113,6 +115,7 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.spectral_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), _ip]
     lib.spectral_get_work.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int]
+    lib.spectral_get_class_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
     _lib = lib
     return lib
 
@@ -350,9 +353,16 @@ class SpectralPlanner:
         return out
 
     def get_work(self, reset: bool = False) -> dict:
-        w = (ctypes.c_double * 4)()
+        w = (ctypes.c_double * NUM_WORK)()
         self._check(self._lib.spectral_get_work(self._h, w, 1 if reset else 0))
-        return dict(admm_iters=w[0], admm_flops=w[1], scenarios=w[2], solved=w[3])
+        return dict(admm_iters=w[0], admm_flops=w[1], scenarios=w[2], solved=w[3], sum_K=w[4], admm_flops_variable=w[5],
+                    **{"admm_flops_class%d" % c: w[6 + c] for c in range(NUM_CLASSES)})
+
+    def get_class_timing(self) -> list:
+        """Summed device ms per solver class (K <= 8, 10, 12, 16, 32) since set_timing(True)."""
+        ms = (ctypes.c_float * NUM_CLASSES)()
+        self._check(self._lib.spectral_get_class_timing(self._h, ms))
+        return [float(x) for x in ms]
 
 
 # ------------------------------------------------------------------ the reference's plugin surface

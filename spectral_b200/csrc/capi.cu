@@ -18,6 +18,8 @@
 #include "qp_anchor.cuh"
 #include "tables.cuh"
 
+static_assert(SPECTRAL_NUM_CLASSES == SP_NUM_CLASSES && SPECTRAL_NUM_WORK >= 6 + SP_NUM_CLASSES, "include/spectral.h");
+
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
 extern "C" int spectral_corridor_prepare(int N, int R, int *configured);                           // corridor.cu
 
@@ -110,33 +112,41 @@ __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a
   }
 }
 
-// `work` accumulates what the QP kernel did, for the roofline accounting of bench.py:
-//   work[0] += ADMM iterations summed over the axis problems of this batch
-//   work[1] += algorithmic flops of those iterations, 72 K^2 + 208 K - 24 per axis-iteration
-//   work[2] += scenarios processed,  work[3] += scenarios solved
+// `work` (SPECTRAL_NUM_WORK doubles) accumulates what the step did, for the roofline accounting of bench.py:
+//   [0] ADMM iterations summed over the axis problems     [1] their flops in the DENSE-operator count, 72 K^2 + 208 K - 24 per
+//   axis-iteration (dense apply of the 6K x 6K inverse + A, A' products; 424 K - 168 above the dense kernels' capacity)
+//   [2] scenarios processed   [3] scenarios solved   [4] sum of K over scenarios with a corridor (corridor kernel output bytes)
+//   [5] the same iterations in the VARIABLE-STRUCTURE count of SURVEY.md 8d, 424 K - 168 per axis-iteration (block-tridiagonal
+//   solve: the algorithmic minimum when no two scenarios share a KKT matrix)   [6 + c] dense-count flops of solver class c
 __global__ void k_finalize(const FinalArgs a, double *work) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  double it = 0.0, fl = 0.0, ok = 0.0, cnt = 0.0;
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double fcls = 0.0;
+  int cls = 0;
   if (b < a.B) {
     finalize_body(a, b);
-    cnt = 1.0;
+    v[2] = 1.0;
     if (a.cstatus[b] == 0) {
-      it = (double)a.axis_iters[2 * b] + (double)a.axis_iters[2 * b + 1];
-      // algorithmic flops per axis-iteration: dense apply of the 6K x 6K inverse + A and A' products,
-      // 2 (6K)^2 + 4 (52K - 6); above the dense kernels' capacity the block-tridiagonal count 424 K - 168
+      const double it = (double)a.axis_iters[2 * b] + (double)a.axis_iters[2 * b + 1];
       const double Kd = (double)a.K[b];
-      fl = it * (a.K[b] <= 16 ? 72.0 * Kd * Kd + 208.0 * Kd - 24.0 : 424.0 * Kd - 168.0);
+      v[0] = it;
+      v[1] = it * (a.K[b] <= 16 ? 72.0 * Kd * Kd + 208.0 * Kd - 24.0 : 424.0 * Kd - 168.0);
+      v[4] = Kd;
+      v[5] = it * (424.0 * Kd - 168.0);
+      cls = lane_class(a.K[b]);
+      fcls = v[1];
       const int s0 = a.axis_status[2 * b], s1 = a.axis_status[2 * b + 1];
-      ok = ((s0 == QP_ST_SOLVED || s0 == QP_ST_INACCURATE) && (s1 == QP_ST_SOLVED || s1 == QP_ST_INACCURATE)) ? 1.0 : 0.0;
+      v[3] = ((s0 == QP_ST_SOLVED || s0 == QP_ST_INACCURATE) && (s1 == QP_ST_SOLVED || s1 == QP_ST_INACCURATE)) ? 1.0 : 0.0;
     }
   }
-  for (int m = 16; m > 0; m >>= 1) {
-    it += __shfl_xor_sync(0xffffffffu, it, m); fl += __shfl_xor_sync(0xffffffffu, fl, m);
-    ok += __shfl_xor_sync(0xffffffffu, ok, m); cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    for (int m = 16; m > 0; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+  if ((threadIdx.x & 31) == 0 && v[2] > 0.0) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) atomicAdd(&work[i], v[i]);
   }
-  if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
-    atomicAdd(&work[0], it); atomicAdd(&work[1], fl); atomicAdd(&work[2], cnt); atomicAdd(&work[3], ok);
-  }
+  if (fcls > 0.0) atomicAdd(&work[6 + cls], fcls);
 }
 
 // K6: (min cost, lowest index) -- two-stage, last block finishes (ticket)
@@ -210,6 +220,7 @@ struct spectral_handle {
   bool timing = false;
   static const int kTimingSlots = 64;  // ring of per-call event sets; nothing synchronises until get_timing
   cudaEvent_t ev[kTimingSlots][SPECTRAL_NUM_KERNELS + 1] = {};
+  cudaEvent_t ev_cls[kTimingSlots][SP_NUM_CLASSES][2] = {};  // around each solver class' kernel, on that class' stream
   long long timed_calls = 0;
   double *work = nullptr;  // device counters, see k_finalize
   // intermediates
@@ -226,6 +237,7 @@ struct spectral_handle {
   double *d_ctrl = nullptr, *d_obj = nullptr, *d_cost = nullptr, *d_samples = nullptr, *d_lu = nullptr;
   size_t d_samples_bytes = 0, d_lu_bytes = 0;
   bool qp_attr_set = false;
+  int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
 };
@@ -285,10 +297,12 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   CK(cudaMalloc(&h->partial, 1024 * sizeof(ArgminPair)));
   CK(cudaMalloc(&h->ticket, 4));
   CK(cudaMemset(h->ticket, 0, 4));
-  CK(cudaMalloc(&h->work, 4 * 8));
-  CK(cudaMemset(h->work, 0, 4 * 8));
+  CK(cudaMalloc(&h->work, SPECTRAL_NUM_WORK * 8));
+  CK(cudaMemset(h->work, 0, SPECTRAL_NUM_WORK * 8));
   for (auto &slot : h->ev)
     for (auto &e : slot) CK(cudaEventCreate(&e));
+  for (auto &slot : h->ev_cls)
+    for (auto &c : slot) { CK(cudaEventCreate(&c[0])); CK(cudaEventCreate(&c[1])); }
   return SPECTRAL_SUCCESS;
 }
 
@@ -302,6 +316,8 @@ extern "C" int spectral_destroy(spectral_handle_t *h) {
   for (auto p : h->d_in) if (p) cudaFree(p);
   for (auto &slot : h->ev)
     for (auto &e : slot) if (e) cudaEventDestroy(e);
+  for (auto &slot : h->ev_cls)
+    for (auto &c : slot) { if (c[0]) cudaEventDestroy(c[0]); if (c[1]) cudaEventDestroy(c[1]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   for (auto &s : h->side) if (s) cudaStreamDestroy(s);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -332,12 +348,26 @@ extern "C" int spectral_get_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_K
   if (calls) *calls = n;
   return SPECTRAL_SUCCESS;
 }
-extern "C" int spectral_get_work(spectral_handle_t *h, double work[4], int reset) {
+extern "C" int spectral_get_class_timing(spectral_handle_t *h, float ms[SPECTRAL_NUM_CLASSES]) {
+  if (!h || !ms) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int n = (int)(h->timed_calls < spectral_handle::kTimingSlots ? h->timed_calls : spectral_handle::kTimingSlots);
+  for (int c = 0; c < SPECTRAL_NUM_CLASSES; c++) ms[c] = 0.f;
+  for (int s = 0; s < n; s++)
+    for (int c = 0; c < h->classes_timed && c < SPECTRAL_NUM_CLASSES; c++) {
+      float t = 0.f;
+      CK(cudaEventSynchronize(h->ev_cls[s][c][1]));
+      CK(cudaEventElapsedTime(&t, h->ev_cls[s][c][0], h->ev_cls[s][c][1]));
+      ms[c] += t;
+    }
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_get_work(spectral_handle_t *h, double work[SPECTRAL_NUM_WORK], int reset) {
   if (!h || !work) return SPECTRAL_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(work, h->work, 4 * 8, cudaMemcpyDeviceToHost));
-  if (reset) CK(cudaMemset(h->work, 0, 4 * 8));
+  CK(cudaMemcpy(work, h->work, SPECTRAL_NUM_WORK * 8, cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(h->work, 0, SPECTRAL_NUM_WORK * 8));
   return SPECTRAL_SUCCESS;
 }
 
@@ -434,11 +464,15 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
     cudaStream_t cs = cls == 0 ? st : h->side[cls - 1];
     if (cls > 0) CK(cudaStreamWaitEvent(cs, h->ev_fork, 0));
     qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls; qa.next = h->counts + SP_NUM_CLASSES + cls;
+    cudaEvent_t *ec = h->ev_cls[h->timed_calls % spectral_handle::kTimingSlots][cls];
+    if (tm) CK(cudaEventRecord(ec[0], cs));
     if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
     else if (cls == 1) CK((h->legacy_qpd ? launch_qpd<10>(h, qa, B, cs) : launch_qpa<10>(h, qa, B, cs)));
     else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));
     else if (cls == 3) CK((launch_qpd<16>(h, qa, B, cs)));
     else CK((launch_qp<32, 2>(h, qa, B, cs)));
+    if (tm) CK(cudaEventRecord(ec[1], cs));
+    h->classes_timed = cls + 1;
     if (cls > 0) {
       CK(cudaEventRecord(h->ev_join[cls - 1], cs));
       CK(cudaStreamWaitEvent(st, h->ev_join[cls - 1], 0));

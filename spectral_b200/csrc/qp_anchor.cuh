@@ -25,6 +25,13 @@
 #include "qp_dense.cuh"
 
 #define QPA_SPW 5  // segments per warp
+// tuning switches (measured on B200, profiles/r2_qpa_variants.md)
+#ifndef QPA_GRP
+#define QPA_GRP(N) (((N) % 24 == 0) ? 24 : (((N) % 20 == 0) ? 20 : 12))  // doubles of g in flight per group in S3
+#endif
+#ifndef QPA_FENCE
+#define QPA_FENCE 0   // scheduling fences between the load runs and the arithmetic (measured: 81.5 k solves/s with, 82.6 k without)
+#endif
 
 template <int N>
 struct QpaIO {
@@ -79,11 +86,15 @@ SP_DEV double qpa_gather(const double vv[5], int lane, int jsrc, double tkv, dou
 }
 
 // A block of n ADMM iterations (out of line: only the hot state is live).
-template <int KC, typename SyncAxisFn>
-SP_DEV_NOINLINE void qpa_block(QpaIO<6 * KC> &io, double *smx, int ta, int axis, int n, double alpha, SyncAxisFn sync_axis_fn) {
+#ifndef QPA_AXIS_TMPL
+#define QPA_AXIS_TMPL 1  // 1: the axis is a template parameter of the block (barrier ids become immediates without predication)
+#endif
+template <int KC, int AX, typename SyncAxisFn>
+SP_DEV_NOINLINE void qpa_block(QpaIO<6 * KC> &io, double *smx, int ta, int axis_rt, int n, double alpha, SyncAxisFn sync_axis_fn) {
+  const int axis = AX >= 0 ? AX : axis_rt;
   using L = QpdLayout<KC>;
   constexpr int N = L::N;
-  constexpr int GRP = (N % 24 == 0) ? 24 : ((N % 20 == 0) ? 20 : 12);
+  constexpr int GRP = QPA_GRP(N);
   static_assert(N % GRP == 0 && GRP % 4 == 0, "g in whole groups");
   int seg, i;
   bool isvar;
@@ -127,7 +138,7 @@ SP_DEV_NOINLINE void qpa_block(QpaIO<6 * KC> &io, double *smx, int ta, int axis,
         double gl[GRP];
 #pragma unroll
         for (int e = 0; e < GRP; e += 2) qpd_lds2(gv + g0 + e, gl[e], gl[e + 1]);
-        qpd_sched_fence();
+        qpd_sched_fence_if<QPA_FENCE>();
 #pragma unroll
         for (int e = 0; e < GRP; e += 4) {
           a0 += G[g0 + e] * gl[e]; a1 += G[g0 + e + 1] * gl[e + 1]; a2 += G[g0 + e + 2] * gl[e + 2]; a3 += G[g0 + e + 3] * gl[e + 3];
@@ -143,7 +154,7 @@ SP_DEV_NOINLINE void qpa_block(QpaIO<6 * KC> &io, double *smx, int ta, int axis,
     {  // S1
       const double c1 = cxp[1], c2 = cxp[2], c3 = cxp[3];
       const double j0 = cpj[0], j1 = cpj[1], j2 = cpj[2], j3 = cpj[3], j4 = cpj[4], j5 = cpj[5];
-      qpd_sched_fence();
+      qpd_sched_fence_if<QPA_FENCE>();
       const double c0 = xt;
       const double d1 = c1 - c0, e1 = c2 - c1, f1_ = c3 - c2;
       const double d2 = e1 - d1, e2 = f1_ - e1;
@@ -372,7 +383,12 @@ SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       it_end = nxt < it_end ? nxt : it_end;
     }
     const bool check = (o.check_every > 0) && (it_end % o.check_every == 0);
-    qpa_block<KC>(io, smx, ta, axis, it_end - it + 1, o.alpha, sync_axis_fn);
+#if QPA_AXIS_TMPL
+    if (axis == 0) qpa_block<KC, 0>(io, smx, ta, 0, it_end - it + 1, o.alpha, sync_axis_fn);
+    else qpa_block<KC, 1>(io, smx, ta, 1, it_end - it + 1, o.alpha, sync_axis_fn);
+#else
+    qpa_block<KC, -1>(io, smx, ta, axis, it_end - it + 1, o.alpha, sync_axis_fn);
+#endif
     iters = it_end;
     it = it_end + 1;
     if (!check) continue;

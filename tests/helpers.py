@@ -256,8 +256,9 @@ def assert_batch_parity(got, ref, label="", need_verified_frac=0.0, ref0=None, m
             di = np.abs(got.iters[ds].astype(np.int64) - ref0["iters"][ds].astype(np.int64))
             eq = float((di == 0).mean())
             stats.update(iters_compared=int(ds.sum()), iters_equal_frac=eq, iters_maxdiff=int(di.max()))
-            assert eq >= min_iters_equal_frac, "%s: iteration count equals the reference-settings oracle's on only %.3f of %d scenarios" % (
-                label, eq, ds.sum())
+            # (count-based so that a tiny batch may hold one borderline scenario: a residual within round-off of eps at a check)
+            assert (di != 0).sum() <= max(1, int(np.floor((1.0 - min_iters_equal_frac) * ds.sum()))), \
+                "%s: iteration count equals the reference-settings oracle's on only %.3f of %d scenarios" % (label, eq, ds.sum())
 
     # ---- numerical comparison of every scenario both sides solve
     both = got.verified() & (ref["status"] <= 1) & (ref["polish"] == 2)

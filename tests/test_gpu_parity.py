@@ -100,6 +100,32 @@ def test_find_traj_drop_in_reproduces_shipped_output(tmp_path, variant, weights,
         os.environ.pop("SPECTRAL_IO_DIR", None)
 
 
+@pytest.mark.parametrize("module,weights,golden_file,tol", [
+    ("trp_wrapper", GOLDEN_W_TRP, "s1_slt_3d_31.txt", (0.0011, 0.0006, 0.0011, 0.0006, 0.0011, 0.0011)),
+    ("cub_wrapper", GOLDEN_W_CUB, "s1_cub_3d_31.txt", (0.024, 0.0006, 0.012, 0.0006, 0.015, 0.0006)),
+])
+def test_unchanged_reference_wrapper_reproduces_shipped_output(tmp_path, monkeypatch, module, weights, golden_file, tol):
+    """Config 1 as SURVEY.md 8d prescribes it: the reference's OWN src/trp_wrapper.py / src/cub_wrapper.py, unmodified,
+    import our .so from their hard-coded path (/home/srujan_d/RISS/code/btrapz/src) and run c1.txt; the file they make
+    the library write is the reference's shipped output to its printed decimals.  Needs /root/reference (skipped on a
+    box that does not have it: reference sources are not copied into this repo)."""
+    from test_host_and_abi import REF_LIB_DIR, _stage_reference_wrapper
+    w = _stage_reference_wrapper(tmp_path, monkeypatch, module)
+    trp = module == "trp_wrapper"
+    write_scenario_text(os.path.join(REF_LIB_DIR, "c_road_s1_2.txt" if trp else "c_road_s1_3.txt"), load_fixture("c1"))
+    cost = w._run_btrapz(w.Params(*weights, 31))
+    assert cost != 100000000000
+    out = read_trajectory_text(os.path.join(REF_LIB_DIR, "s1_slt_3d_31.txt" if trp else "s1_cub_3d_31.txt"))
+    gold = read_trajectory_text(os.path.join(H.GOLDEN, golden_file))
+    assert out.shape == gold.shape
+    for c in range(6):
+        assert np.abs(out[:, 1 + c] - gold[:, 1 + c]).max() <= tol[c]
+    with open(os.path.join(REF_LIB_DIR, "weights.txt"), "w") as f:
+        f.write("\t".join(str(v) for v in WEIGHTS_FILE) + "\n")
+    assert w.find_traj() is True   # the module's own entry: reads weights.txt, iteration = 3 (trp_wrapper.py:99-121)
+    assert os.path.exists(os.path.join(REF_LIB_DIR, "s1_slt_3d_3.txt" if trp else "s1_cub_3d_3.txt"))
+
+
 def test_find_traj_failure_sentinel(tmp_path):
     os.environ["SPECTRAL_IO_DIR"] = str(tmp_path)
     try:

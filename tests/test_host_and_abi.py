@@ -175,3 +175,54 @@ def test_config3_groups_share_one_kkt_structure():
     tail = config3(16, groups=G, first=B - 16)
     for a, b in zip(tail.arrays(), batch.arrays()):
         assert np.array_equal(a, b[B - 16:])
+
+
+# ---------------------------------------------------------------- the reference's OWN wrapper modules, unchanged
+REF_SRC = "/root/reference/src"
+REF_LIB_DIR = "/home/srujan_d/RISS/code/btrapz/src"   # the literal path the wrappers CDLL() (trp_wrapper.py:45, cub_wrapper.py)
+
+
+def _stage_reference_wrapper(tmp_path, monkeypatch, module):
+    """Installs OUR libtrp.so / libcub.so / libspectral.so at the literal path the reference's wrapper loads from, puts a
+    stub `optuna` on sys.path (the wrappers import it at module top, trp_wrapper.py:3; it is not installed here) and imports
+    the reference's module from /root/reference/src WITHOUT editing it."""
+    import importlib
+    import shutil
+    import sys
+    if not os.path.isdir(REF_SRC):
+        pytest.skip("/root/reference is not present on this machine (the wrapper sources may not be copied into the repo)")
+    try:
+        os.makedirs(REF_LIB_DIR, exist_ok=True)
+    except OSError:
+        pytest.skip("cannot create " + REF_LIB_DIR)
+    for name in ("libspectral.so", "libtrp.so", "libcub.so"):
+        shutil.copy(api.lib_path(name), os.path.join(REF_LIB_DIR, name))
+    stub = tmp_path / "stub"
+    stub.mkdir()
+    (stub / "optuna.py").write_text("def create_study(*a, **k):\n    raise RuntimeError('stub')\n")
+    monkeypatch.syspath_prepend(str(stub))
+    monkeypatch.syspath_prepend(REF_SRC)
+    sys.modules.pop(module, None)
+    return importlib.import_module(module)
+
+
+@pytest.mark.parametrize("module", ["trp_wrapper", "cub_wrapper"])
+def test_unchanged_reference_wrapper_binds_our_library(tmp_path, monkeypatch, module):
+    """src/trp_wrapper.py / src/cub_wrapper.py (unmodified) load our drop-in .so from their hard-coded path and bind
+    find_traj(POINTER(Params)) -> c_double (trp_wrapper.py:45-54); their Params is our SpectralParams byte for byte.
+    Without a GPU the call itself must FAIL LOUDLY (sentinel 1e11 -> the wrapper's find_traj() returns False), never
+    compute on the CPU.  The numerical comparison through the same modules is the GPU test
+    test_gpu_parity.py::test_unchanged_reference_wrapper_reproduces_shipped_output."""
+    w = _stage_reference_wrapper(tmp_path, monkeypatch, module)
+    assert w.cdll._name == os.path.join(REF_LIB_DIR, "libtrp.so" if module == "trp_wrapper" else "libcub.so")
+    assert ctypes.sizeof(w.Params) == ctypes.sizeof(api.Params) == 88
+    for (n0, t0), (n1, t1) in zip(w.Params._fields_, api.Params._fields_):
+        assert n0 == n1 and t0 is t1 and getattr(w.Params, n0).offset == getattr(api.Params, n1).offset
+    assert w._run_btrapz.restype is ctypes.c_double and w._run_btrapz.argtypes == (ctypes.POINTER(w.Params),)
+    import torch
+    if not torch.cuda.is_available():
+        from spectral_b200.scenarios import load_fixture
+        from spectral_b200.wire import write_scenario_text
+        write_scenario_text(os.path.join(REF_LIB_DIR, "c_road_s1_2.txt" if module == "trp_wrapper" else "c_road_s1_3.txt"),
+                            load_fixture("c1"))
+        assert w._run_btrapz(w.Params(35.73, 41.61, 25.57, 41.59, 0.12, 10.04, 0.0, 0.0, 7.27, 32.13, 31)) == 100000000000

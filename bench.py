@@ -39,6 +39,21 @@ BATCH = 1024
 SEED_NOTE = "config2: c1.txt base, cub, 1024 obstacle-perturbed copies/step/GPU, seed 20230531"
 
 
+def workload(cfg, groups=8, shared=True):
+    """The bench workloads.  2 = BASELINE configs[1], the default and the metric's config; 3 = configs[2]."""
+    from spectral_b200.scenarios import GOLDEN_W_CUB, WEIGHTS_FILE, config2, config3
+    if cfg == 2:
+        return dict(name=SEED_NOTE, batch=BATCH, variant="cub", weights=GOLDEN_W_CUB, make=lambda n, first: config2(n, first=first),
+                    options={}, pool=16, streams=4)
+    if cfg == 3:
+        return dict(name="config3: c2.txt base, trp, 65536 synthetic obstacle/time-allocation variants per step and GPU in %d shared-KKT "
+                         "groups, seed 20230601; %s" % (groups, "shared-KKT tiles of 8 on FP64 DMMA (SpectralOptions.shared_kkt = 1)" if shared
+                                                        else "per-scenario kernels (shared_kkt = 0)"),
+                    batch=65536, variant="trp", weights=WEIGHTS_FILE, make=lambda n, first: config3(n, groups=groups, first=first),
+                    options=dict(shared_kkt=1) if shared else {}, pool=2, streams=2)
+    raise SystemExit("bench.py: --config must be 2 or 3")
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -105,7 +120,7 @@ def _host_threads():
         return os.cpu_count() or 1
 
 
-def _cpu_reference(batch, weights, n_scen, threads):
+def _cpu_reference(batch, weights, n_scen, threads, variant="cub"):
     """The reference's CPU implementation of the path on `n_scen` scenarios: oracle/_ref (the reference's own
     sources + OSQP restatement) when present, else the plain-C port.  Returns (seconds, kind, result)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -115,7 +130,7 @@ def _cpu_reference(batch, weights, n_scen, threads):
     # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1, which an OpenMP default would obey
     threads = threads if threads > 0 else _host_threads()
     t0 = time.perf_counter()
-    r = po.solve_batch("cub", sub, weights, mode=0, nthreads=threads, kind=kind)
+    r = po.solve_batch(variant, sub, weights, mode=0, nthreads=threads, kind=kind)
     return time.perf_counter() - t0, kind, r
 
 
@@ -124,14 +139,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from spectral_b200.scenarios import GOLDEN_W_CUB, config2
+    wl = workload(args.config, args.groups, not args.no_shared)
     cores = _host_threads()
     sample = 256
-    batch = config2(BATCH)
+    batch = wl["make"](sample, 0)
     times = []
     kind = "port"
     for i in range(args.warmup + args.steps):
-        dt, kind, _ = _cpu_reference(batch, GOLDEN_W_CUB, sample, 0)
+        dt, kind, _ = _cpu_reference(batch, wl["weights"], sample, 0, wl["variant"])
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
@@ -139,10 +154,11 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": SEED_NOTE, "batch_per_gpu": BATCH, "variant": "cub", "n_knots": 71, "n_regions": 2},
+            "config": {"workload": wl["name"], "batch_per_gpu": wl["batch"], "variant": wl["variant"], "n_knots": batch.n_knots,
+                       "n_regions": batch.n_regions},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "first %d scenarios of the 1024-scenario batch per step, OSQP settings of the "
-                                       "reference (eps 1e-5, max_iter 5000), OpenMP over scenarios" % sample},
+                             "sample": "first %d scenarios of the %d-scenario batch per step, OSQP settings of the "
+                                       "reference (eps 1e-5, max_iter 5000), OpenMP over scenarios" % (sample, wl["batch"])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -152,7 +168,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from spectral_b200 import api
-    from spectral_b200.scenarios import GOLDEN_W_CUB, config2
+    wl = workload(args.config, args.groups, not args.no_shared)
+    VAR, W_VEC = wl["variant"], wl["weights"]
+    base_opt = api.default_options(**wl["options"]) if wl["options"] else None
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,23 +182,24 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, POOL = BATCH, args.pool
+    B = wl["batch"]
+    POOL = args.pool if args.pool > 0 else wl["pool"]
     k_max = 16
     # one handle (= one set of intermediates + one stream) per in-flight step: a 1024-scenario batch fills only part
     # of a B200 (2 CTAs/SM x 148 SMs = 296 scenarios in flight, 3.5 waves with a ragged tail), so consecutive steps
     # are enqueued round-robin on `streams` CUDA streams and overlap
-    NS = max(1, args.streams)
+    NS = max(1, args.streams if args.streams > 0 else wl["streams"])
     planners = [api.SpectralPlanner(device=local, max_batch=B, n_max=128, r_max=8, k_max=k_max) for _ in range(NS)]
     planner = planners[0]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     # ---- synthetic inputs: POOL distinct batches per rank, resident in HBM
     first = rank * POOL * B
-    big = config2(POOL * B, first=first)
+    big = wl["make"](POOL * B, first)
     N, R, delta = big.n_knots, big.n_regions, big.delta_t
     names = ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars")
     host = {k: np.ascontiguousarray(a) for k, a in zip(names, big.arrays())}
     resident = {k: torch.from_numpy(a).to(dev) for k, a in host.items()}
-    w_dev = torch.tensor(GOLDEN_W_CUB, dtype=torch.float64, device=dev)
+    w_dev = torch.tensor(W_VEC, dtype=torch.float64, device=dev)
     outs = [planner.alloc_device_outputs(B) for _ in range(POOL)]
     best_cost = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(NS)]
     best_idx = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(NS)]
@@ -201,7 +220,7 @@ def run_ours(args):
         s = i % POOL
         j = (i % NS) if lane is None else lane
         with torch.cuda.stream(streams[j]):
-            planners[j].solve_device("cub", N, R, delta, slots[s], outs[s], options=options)
+            planners[j].solve_device(VAR, N, R, delta, slots[s], outs[s], options=options if options is not None else base_opt)
             planners[j].argmin_device(outs[s]["a_cost"], first + s * B, best_cost[j], best_idx[j])
             if world > 1:  # the path's only exchange: (cost, index) arg-min gather
                 mine = torch.stack([best_cost[j][0], best_idx[j][0].to(torch.float64)])
@@ -224,6 +243,7 @@ def run_ours(args):
         step(args.warmup + i, lane=0)
     barrier()
     kt = planner.get_timing()
+    kt_cls = planner.get_class_timing()
     planner.set_timing(False)
     work_a = planner.get_work(reset=True)
     # ---- pass B (the timed region): exactly `steps` steps, round-robin over the streams
@@ -260,7 +280,7 @@ def run_ours(args):
 
     # ---- supplementary (not the headline): the same timed loop with SpectralOptions.infeasibility_precheck = 1, i.e.
     #      provably empty corridors fail at once instead of burning up to max_iter ADMM iterations like the reference
-    pre_opt = api.default_options(infeasibility_precheck=1)
+    pre_opt = api.default_options(infeasibility_precheck=1, **wl["options"])
     for i in range(NS):
         step(i, options=pre_opt)
     barrier()
@@ -296,7 +316,7 @@ def run_ours(args):
         return ScenarioBatch(N, R, delta, *[host[k][s * B:(s + 1) * B] for k in names])
 
     hb = [host_batch(i) for i in range(POOL)]
-    w_host = np.array(GOLDEN_W_CUB)
+    w_host = np.array(W_VEC)
     # every planner owns page-locked staging buffers; a step's inputs are copied into them (host memcpy, timed) and
     # from there to the device
     best = []
@@ -304,7 +324,7 @@ def run_ours(args):
         pl = planners[i % NS]
         if getattr(pl, "_pending", None) is not None:
             pl.wait()
-        pl.solve_async("cub", hb[i % POOL], w_host)
+        pl.solve_async(VAR, hb[i % POOL], w_host, options=base_opt)
     for pl in planners:
         if getattr(pl, "_pending", None) is not None:
             pl.wait()
@@ -315,7 +335,7 @@ def run_ours(args):
         if getattr(pl, "_pending", None) is not None:
             res = pl.wait()
             best.append(float(res.a_cost.min()))  # the step's result is read on the host
-        pl.solve_async("cub", hb[(args.warmup + i) % POOL], w_host)
+        pl.solve_async(VAR, hb[(args.warmup + i) % POOL], w_host, options=base_opt)
     for pl in planners:
         if getattr(pl, "_pending", None) is not None:
             res = pl.wait()
@@ -337,18 +357,39 @@ def run_ours(args):
         qp_ms = kt["qp"] / calls            # pass A: mean per step of the QP stage (the solver classes of one step, forked streams)
         cor_ms = kt["corridor"] / calls
         flops_per_step = work_a["admm_flops"] / max(na, 1)
+        flops_var_per_step = work_a["admm_flops_variable"] / max(na, 1)
         iters_per_step = work["admm_iters"] / max(args.steps, 1)
         achieved_tf = flops_per_step / (qp_ms * 1e-3) / 1e12 if qp_ms > 0 else 0.0
-        cor_bytes = B * (8 * (4 * R * N + 2 * N) + 112 * 8 + 4)  # bounds + refs in, K cubes + K out
+        achieved_var_tf = flops_var_per_step / (qp_ms * 1e-3) / 1e12 if qp_ms > 0 else 0.0
+        # corridor kernel: algorithmic bytes with the MEASURED segment counts (work counter sum_K), SURVEY.md 8d
+        sum_k_step = work_a["sum_K"] / max(na, 1)
+        cor_bytes = B * (8 * (4 * R * N + 2 * N) + 4) + 112 * sum_k_step
         cor_gbs = cor_bytes / (cor_ms * 1e-3) / 1e9 if cor_ms > 0 else 0.0
-        # CPU baseline: bounded sample of the same workload on the host cores
-        cpu_sample = 128
-        dt, kind, _ = _cpu_reference(hb[0], w_host, cpu_sample, 0)
+        # ncu-measured DRAM traffic per launch, if a committed profile of THIS build's kernels exists (tools/make_profiles.py)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        except Exception:
+            pass
+        cls_names = ("K<=8", "K<=10", "K<=12", "K<=16", "K<=32")
+        cls_kern = ("k_qps (shared-KKT DMMA)" if wl["options"].get("shared_kkt") else "k_qpa<8>", "k_qpa<10>", "k_qpd<12>", "k_qpd<16>", "k_qp<32,2>")
+        per_class = []
+        for c in range(5):
+            ms_c = kt_cls[c] / calls
+            fl_c = work_a["admm_flops_class%d" % c] / max(na, 1)
+            if fl_c > 0 and ms_c > 0:
+                per_class.append({"class": cls_names[c], "kernel": cls_kern[c], "ms_per_step": ms_c, "flops_per_step": fl_c,
+                                  "achieved_tflops": fl_c / (ms_c * 1e-3) / 1e12, "frac": fl_c / (ms_c * 1e-3) / 1e12 / fp64_peak if fp64_peak else None})
+        # CPU baseline: the full batch of one step (bounded: <= 1024 scenarios) on all host cores
+        cpu_sample = min(B, 1024)
+        dt, kind, _ = _cpu_reference(hb[0], w_host, cpu_sample, 0, VAR)
+        ksum = max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9)
+        dmma = bool(wl["options"].get("shared_kkt"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": SEED_NOTE, "batch_per_gpu": B, "variant": "cub", "n_knots": N, "n_regions": R,
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "variant": VAR, "n_knots": N, "n_regions": R,
                        "k_max": k_max, "streams": NS,
                        "l2": "inputs larger than L2: pool of %d distinct batches, %.0f MB in+out per rank" % (POOL, pool_mb),
                        "solved_fraction": solved_frac, "admm_iters_per_s": world * iters_per_step / (ms_max / args.steps * 1e-3),
@@ -358,34 +399,43 @@ def run_ours(args):
                                    "fails provably empty corridors before the ADMM loop; the reference has no such test",
                            "value": pre_value, "unit": UNIT, "solved_fraction": pre_work["solved"] / max(pre_work["scenarios"], 1.0),
                            "mean_axis_iters": pre_work["admm_iters"] / max(args.steps, 1) / (2 * B)}},
-            "roofline": {"kernel": "k_qpd (batched dense-operator ADMM + polish; all solver classes of one step)", "bound": "fp64",
+            "roofline": {"kernel": ("k_qps (shared-KKT tiles, X~ = G [g1..g8] on mma.sync.m8n8k4.f64) + the per-scenario kernels of K > 8" if dmma else
+                                    "k_qpa<8|10> + k_qpd<12|16> (batched dense-operator ADMM + polish; all solver classes of one step)"),
+                         "bound": "tensor" if dmma else "fp64",
                          "achieved": achieved_tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the k_qpd<8> launch of one 1024-scenario step
-                         # (703 live CTAs; ncu --set full, profiles/r1_qpd_full.md: 3.2 MB read + 19.2 MB written): stack/local-memory write-back, the
-                         # ADMM state itself never leaves shared memory and registers
-                         "traffic": 22.4e6,
-                         "peak_source": "FP64 FMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch from the committed ncu
+                         # capture of this build (profiles/r2_traffic.json, written by tools/make_profiles.py), else null
+                         "traffic": traffic.get("k_qps" if dmma else "k_qpa<8>"),
+                         "traffic_source": traffic.get("source"),
+                         "peak_source": "FP64 FMA probe kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry; the DMMA probe "
+                                        "profiles/r1_dmma_probe.md measured 37.1 TFLOP/s on the tensor pipe vs 34.9 on the FMA pipe)",
                          "ms_per_launch_group": qp_ms, "flops_per_step": flops_per_step,
-                         "note": "timed on one stream (pass A, %d steps) with CUDA events around the QP stage; the headline value overlaps %d steps" % (na, NS)},
+                         "count": "dense-operator count 72 K^2 + 208 K - 24 flops per axis-iteration (what the kernels execute)",
+                         "variable_structure_count": {"flops_per_step": flops_var_per_step, "achieved": achieved_var_tf,
+                                                      "frac": achieved_var_tf / fp64_peak if fp64_peak else None,
+                                                      "note": "SURVEY.md 8d count 424 K - 168 per axis-iteration (block-tridiagonal solve): "
+                                                              "the algorithmic minimum when no two scenarios share a KKT matrix"},
+                         "per_class": per_class,
+                         "note": "timed on one stream (pass A, %d steps) with CUDA events around the QP stage; the headline value overlaps %d steps; "
+                                 "per_class times are events on each class' own stream (classes overlap)" % (na, NS)},
             "roofline_corridor": {"kernel": "k_corridor", "bound": "hbm", "achieved": cor_gbs, "peak": peaks.get("hbm_gbs"),
                                   "unit": "GB/s", "frac": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                                  # ncu --set full at B = 65 536 (profiles/r1_small_kernels.md): 425 MB DRAM traffic per
-                                  # launch against 431 MB algorithmic, i.e. 6.49 KB per scenario -> per 1024-scenario launch
-                                  "traffic": 6.49e3 * B, "peak_source": peak_src, "ms_per_launch": cor_ms,
-                                  "note": "bound by the lane-0 replay of the sequential selection logic, not by HBM: 0.065 of peak even at B = 65 536 (1.0 ms)"},
+                                  "traffic": traffic.get("k_corridor"), "traffic_source": traffic.get("source"),
+                                  "algorithmic_bytes_per_launch": cor_bytes, "mean_K": sum_k_step / max(B, 1),
+                                  "peak_source": peak_src, "ms_per_launch": cor_ms,
+                                  "note": "bound by the lane-0 replay of the sequential selection logic, not by HBM (profiles/r1_small_kernels.md)"},
             "kernel_ms_per_step": {k: kt[k] / calls for k in ("tables", "corridor", "classify", "qp", "finalize")},
-            # every kernel of the step with the resource that bounds it (ncu evidence: profiles/r1_qpd_full.md,
-            # profiles/r1_small_kernels.md); shares from the CUDA-event ring of pass A
+            # every kernel of the step with the resource that bounds it; shares from the CUDA-event ring of pass A
             "kernels": [
-                {"kernel": "k_qpd<8|10|12|16> (ADMM)", "bound": "fp64 / shared-memory pipe / latency", "share": kt["qp"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9),
+                {"kernel": "QP stage (k_qps / k_qpa / k_qpd / k_qp)", "bound": "fp64 pipe / shared-memory pipe / latency", "share": kt["qp"] / ksum,
                  "frac_of_fp64_peak": achieved_tf / fp64_peak if fp64_peak else None},
-                {"kernel": "k_corridor", "bound": "hbm", "share": kt["corridor"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9),
+                {"kernel": "k_corridor", "bound": "hbm", "share": kt["corridor"] / ksum,
                  "frac_of_hbm_peak": cor_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
-                {"kernel": "k_finalize", "bound": "latency (8 CTAs)", "share": kt["finalize"] / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9)},
-                {"kernel": "k_tables + k_classify", "bound": "launch latency (one CTA each)", "share": (kt["tables"] + kt["classify"]) / max(sum(kt[k] for k in ("tables", "corridor", "classify", "qp", "finalize")), 1e-9)}],
+                {"kernel": "k_finalize", "bound": "latency", "share": kt["finalize"] / ksum},
+                {"kernel": "k_tables + k_classify", "bound": "launch latency (one CTA each)", "share": (kt["tables"] + kt["classify"]) / ksum}],
             "cpu_baseline": {"value": cpu_sample / dt, "unit": UNIT, "cores": _host_threads(), "kind": kind,
-                             "sample": "first %d scenarios of one 1024-scenario batch, reference OSQP settings" % cpu_sample},
+                             "sample": "first %d scenarios of one %d-scenario batch, reference OSQP settings" % (cpu_sample, B)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk,
         }
@@ -400,8 +450,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--pool", type=int, default=16)
-    ap.add_argument("--streams", type=int, default=4, help="steps in flight (one handle + CUDA stream each)")
+    ap.add_argument("--pool", type=int, default=0, help="distinct batches resident per rank (0: the workload's default)")
+    ap.add_argument("--streams", type=int, default=0, help="steps in flight (one handle + CUDA stream each; 0: the workload's default)")
+    ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA)")
+    ap.add_argument("--no-shared", action="store_true", help="config 3 through the per-scenario kernels (A/B of the shared-KKT path)")
+    ap.add_argument("--groups", type=int, default=8, help="config 3: number of shared-KKT groups (1, 8, 64)")
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     args = ap.parse_args()
     if args.impl == "reference":

@@ -137,6 +137,13 @@ typedef struct {
                            problems its OSQP either certifies infeasibility late or stops at max_iter, sometimes with the
                            status "solved inaccurate" and a constraint-violating trajectory. */
   double precheck_margin; /* 1e-3: an interval gap must exceed this to count */
+  int shared_kkt;         /* 0 (default): every scenario runs OSQP's own iteration (per-scenario Ruiz scaling and adaptive rho).
+                             1: scenarios with K <= 8 that share one KKT structure (same K, same segment durations, same weights; only
+                             bounds, initial state and references differ -- BASELINE configs[2]) are solved in tiles of 8 against ONE
+                             reduced-KKT inverse, the per-iteration solve being a multi-right-hand-side product on the FP64 tensor cores
+                             (mma.sync m8n8k4 f64).  Same QP, same ADMM, same termination test, but the scaling is the tile's first
+                             member's and rho adapts per tile: the optimum and the decided solved / failed classes are the reference's,
+                             the iteration counts are not OSQP's. */
 } SpectralOptions;
 
 typedef struct spectral_handle spectral_handle_t;

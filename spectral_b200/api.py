@@ -66,7 +66,7 @@ class SpectralOptions(ctypes.Structure):
                 ("adaptive_rho_interval", ctypes.c_int), ("adaptive_rho_tolerance", ctypes.c_double),
                 ("polish", ctypes.c_int), ("polish_delta", ctypes.c_double), ("polish_refine_iter", ctypes.c_int),
                 ("polish_rounds", ctypes.c_int), ("infeasibility_precheck", ctypes.c_int),
-                ("precheck_margin", ctypes.c_double)]
+                ("precheck_margin", ctypes.c_double), ("shared_kkt", ctypes.c_int)]
 
 
 class Params(ctypes.Structure):

@@ -4,6 +4,7 @@
 // There is no CPU path in this library: every entry point needs a CUDA device and reports
 // SPECTRAL_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include "qp.cuh"
 #include "qp_dense.cuh"
 #include "qp_anchor.cuh"
+#include "qp_shared.cuh"
 #include "tables.cuh"
 
 static_assert(SPECTRAL_NUM_CLASSES == SP_NUM_CLASSES && SPECTRAL_NUM_WORK >= 6 + SP_NUM_CLASSES, "include/spectral.h");
@@ -110,6 +112,71 @@ __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a
                        else asm volatile("bar.sync 2, %0;" ::"n"(QpdLayout<KC>::TA) : "memory");
                      });
   }
+}
+
+// ------------------------------------------------------------------ shared-KKT path (qp_shared.cuh)
+// structure key of a scenario of the K <= 8 class: (K, the bit patterns of t_k, the weights when they are per scenario)
+__global__ void k_qps_keys(const int *cstatus, const int *K, const SpectralCube *segs, int k_max, const double *weights, int wstride, int B,
+                           unsigned long long *keys, int *ids, int *leader_tile) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  unsigned long long h = ~0ull;
+  if (cstatus[b] == 0 && K[b] >= 1 && K[b] <= QPS_KC) {
+    h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)K[b];
+    auto mix = [&h](unsigned long long w) {
+      h ^= w; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29; h *= 0x94D049BB133111EBull; h ^= h >> 32;
+    };
+    for (int k = 0; k < K[b]; k++) mix((unsigned long long)__double_as_longlong(segs[(size_t)b * k_max + k].t));
+    if (wstride)
+      for (int i = 0; i < 10; i++) mix((unsigned long long)__double_as_longlong(weights[(size_t)b * 10 + i]));
+    if (h == ~0ull) h = 0x1234567ull;
+  }
+  keys[b] = h; ids[b] = b; leader_tile[b] = -1;
+}
+__global__ void k_qps_heads(const unsigned long long *keys, int B, int *head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  head[i] = (keys[i] != ~0ull && (i == 0 || keys[i] != keys[i - 1])) ? i : 0;
+}
+__global__ void k_qps_flags(const unsigned long long *keys, const int *gstart, int B, int *flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  flag[i] = (keys[i] != ~0ull && ((i - gstart[i]) % QPS_TILE) == 0) ? 1 : 0;
+}
+__global__ void k_qps_emit(const unsigned long long *keys, const int *ids, const int *flag, const int *tidx, int B, int *tile_start,
+                           int *tile_count, int *n_tiles, int *leader_tile) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (flag[i]) {
+    int c = 1;
+    while (c < QPS_TILE && i + c < B && keys[i + c] == keys[i]) c++;
+    tile_start[tidx[i]] = i; tile_count[tidx[i]] = c;
+    leader_tile[ids[i]] = tidx[i];
+  }
+  if (i == B - 1) *n_tiles = tidx[i] + flag[i];
+}
+__global__ void __launch_bounds__(64) k_qps_prepare(const QpsArgs A, const int *leader_tile) {
+  extern __shared__ double qp_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  qps_prepare_body(A, leader_tile, blockIdx.x * 2 + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
+}
+__global__ void __launch_bounds__(64) k_qps(const QpsArgs A) {
+  extern __shared__ __align__(16) double qps_smem[];
+  __shared__ int s_tile;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(A.tile_next, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    __syncthreads();
+    if (tile >= *A.n_tiles) return;
+    qps_tile_body(A, tile, blockIdx.x, threadIdx.x, qps_smem, []() { __syncthreads(); });
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(64) k_qps_finish(const QpsArgs A) {
+  extern __shared__ double qp_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  qps_finish_body(A, blockIdx.x * 2 + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32);
 }
 
 // `work` (SPECTRAL_NUM_WORK doubles) accumulates what the step did, for the roofline accounting of bench.py:
@@ -237,6 +304,14 @@ struct spectral_handle {
   double *d_ctrl = nullptr, *d_obj = nullptr, *d_cost = nullptr, *d_samples = nullptr, *d_lu = nullptr;
   size_t d_samples_bytes = 0, d_lu_bytes = 0;
   bool qp_attr_set = false;
+  // shared-KKT path (allocated on first use)
+  unsigned long long *qs_keys = nullptr, *qs_keys2 = nullptr;
+  int *qs_ids = nullptr, *qs_ids2 = nullptr, *qs_tmp = nullptr /* head, gstart, flag, tidx: 4 x B */, *qs_tile = nullptr /* start, count: 2 x B */,
+      *qs_leader = nullptr, *qs_misc = nullptr /* n_tiles, tile_next */, *qs_st = nullptr;
+  QpsTileBlk *qs_blk = nullptr;
+  double *qs_lu = nullptr, *qs_qv = nullptr, *qs_w = nullptr, *qs_x = nullptr, *qs_fs = nullptr;
+  void *qs_cub = nullptr;
+  size_t qs_cub_bytes = 0;
   int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
@@ -257,7 +332,7 @@ extern "C" void spectral_default_options(SpectralOptions *o) {
   o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
   o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
   o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
-  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3;
+  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3; o->shared_kkt = 0;
 }
 
 extern "C" const char *spectral_last_error(const spectral_handle_t *h) { return h ? h->err.c_str() : "null handle"; }
@@ -309,6 +384,9 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
 extern "C" int spectral_destroy(spectral_handle_t *h) {
   if (!h) return SPECTRAL_ERR_INVALID;
   cudaSetDevice(h->device);
+  void *qsb[] = {h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, h->qs_tmp, h->qs_tile, h->qs_leader, h->qs_misc, h->qs_st, h->qs_blk, h->qs_lu,
+                 h->qs_qv, h->qs_w, h->qs_x, h->qs_cub, h->qs_fs};
+  for (void *p : qsb) if (p) cudaFree(p);
   void *bufs[] = {h->cstatus, h->lists, h->counts, h->axis_status, h->axis_iters, h->axis_polished, h->axis_obj, h->mqm,
                   h->partial, h->ticket, h->work, h->d_K, h->d_status, h->d_iters, h->d_flags, h->d_npts, h->d_segs, h->d_ctrl,
                   h->d_obj, h->d_cost, h->d_samples, h->d_lu};
@@ -392,6 +470,60 @@ static cudaError_t launch_qpa(spectral_handle *h, const QpArgs &qa, int B, cudaS
   return cudaGetLastError();
 }
 
+// Shared-KKT path for the K <= 8 class: structure keys -> sort -> tiles of <= 8 scenarios -> prepare -> tile ADMM (DMMA) -> finish
+static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, int B, const SpectralInputs *in, cudaStream_t st) {
+  const size_t Bm = (size_t)h->max_batch, km = (size_t)h->k_max;
+  if (!h->qs_keys) {
+    CK(cudaMalloc(&h->qs_keys, Bm * 8)); CK(cudaMalloc(&h->qs_keys2, Bm * 8));
+    CK(cudaMalloc(&h->qs_ids, Bm * 4)); CK(cudaMalloc(&h->qs_ids2, Bm * 4));
+    CK(cudaMalloc(&h->qs_tmp, 4 * Bm * 4)); CK(cudaMalloc(&h->qs_tile, 2 * Bm * 4));
+    CK(cudaMalloc(&h->qs_leader, Bm * 4)); CK(cudaMalloc(&h->qs_misc, 2 * 4)); CK(cudaMalloc(&h->qs_st, 4 * Bm * 4));
+    CK(cudaMalloc(&h->qs_blk, 2 * Bm * sizeof(QpsTileBlk)));
+    CK(cudaMalloc(&h->qs_lu, Bm * 2 * km * QP_ROWS * 2 * 8));
+    CK(cudaMalloc(&h->qs_fs, (size_t)2 * h->sm_count * QPS_FS_DOUBLES * 8));
+    CK(cudaMalloc(&h->qs_qv, Bm * 2 * 8 * 6 * 8)); CK(cudaMalloc(&h->qs_w, Bm * 2 * 8 * QP_ROWS * 8)); CK(cudaMalloc(&h->qs_x, Bm * 2 * QPS_N * 8));
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, h->max_batch);
+    cub::DeviceScan::InclusiveScan(nullptr, t2, h->qs_tmp, h->qs_tmp, cub::Max(), h->max_batch);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, h->qs_tmp, h->qs_tmp, h->max_batch);
+    h->qs_cub_bytes = t1 > t2 ? (t1 > t3 ? t1 : t3) : (t2 > t3 ? t2 : t3);
+    CK(cudaMalloc(&h->qs_cub, h->qs_cub_bytes));
+  }
+  int *head = h->qs_tmp, *gstart = h->qs_tmp + Bm, *flag = h->qs_tmp + 2 * Bm, *tidx = h->qs_tmp + 3 * Bm;
+  int *tile_start = h->qs_tile, *tile_count = h->qs_tile + Bm;
+  const int nb = (B + 255) / 256;
+  CK(cudaMemsetAsync(h->qs_misc, 0, 8, st));
+  k_qps_keys<<<nb, 256, 0, st>>>(cstatus, qa.K, qa.segs, h->k_max, in->weights, in->weights_stride, B, h->qs_keys, h->qs_ids, h->qs_leader);
+  size_t tb = h->qs_cub_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(h->qs_cub, tb, h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, B, 0, 64, st));
+  k_qps_heads<<<nb, 256, 0, st>>>(h->qs_keys2, B, head);
+  tb = h->qs_cub_bytes;
+  CK(cub::DeviceScan::InclusiveScan(h->qs_cub, tb, head, gstart, cub::Max(), B, st));
+  k_qps_flags<<<nb, 256, 0, st>>>(h->qs_keys2, gstart, B, flag);
+  tb = h->qs_cub_bytes;
+  CK(cub::DeviceScan::ExclusiveSum(h->qs_cub, tb, flag, tidx, B, st));
+  k_qps_emit<<<nb, 256, 0, st>>>(h->qs_keys2, h->qs_ids2, flag, tidx, B, tile_start, tile_count, h->qs_misc, h->qs_leader);
+  QpsArgs A;
+  A.q = qa; A.q.lu = h->qs_lu;
+  A.tile_start = tile_start; A.tile_count = tile_count; A.n_tiles = h->qs_misc; A.sorted = h->qs_ids2; A.tile_next = h->qs_misc + 1;
+  A.fs_scratch = h->qs_fs;
+  A.blk = h->qs_blk; A.qv = h->qs_qv; A.wrows = h->qs_w; A.xout = h->qs_x; A.st = h->qs_st;
+  const size_t sm_pf = 2 * (size_t)QP_SMEM_PER_WARP;
+  CK(cudaFuncSetAttribute(k_qps_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
+  CK(cudaFuncSetAttribute(k_qps_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
+  CK(cudaFuncSetAttribute(k_qps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QpsSmem::BYTES));
+  const int pf_blocks = (B + 3) / 4;  // two scenarios per warp, two warps per block
+  k_qps_prepare<<<pf_blocks, 64, sm_pf, st>>>(A, h->qs_leader);
+  const int per_sm = 2 * (QpsSmem::BYTES + 1024 + 16) <= 227 * 1024 ? 2 : 1;
+  const int tiles_max = (B + 0) / 1;
+  const int grid = tiles_max < per_sm * h->sm_count ? tiles_max : per_sm * h->sm_count;
+  k_qps<<<grid, 64, QpsSmem::BYTES, st>>>(A);
+  k_qps_finish<<<pf_blocks, 64, sm_pf, st>>>(A);
+  h->launches += 8;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
 template <int LPA, int WPB>
 static cudaError_t launch_qp(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
   constexpr int G = 32 / LPA;
@@ -466,7 +598,8 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
     qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls; qa.next = h->counts + SP_NUM_CLASSES + cls;
     cudaEvent_t *ec = h->ev_cls[h->timed_calls % spectral_handle::kTimingSlots][cls];
     if (tm) CK(cudaEventRecord(ec[0], cs));
-    if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
+    if (cls == 0 && opt.shared_kkt) { const int rc = launch_qps(h, qa, h->cstatus, B, in, cs); if (rc) return rc; }
+    else if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
     else if (cls == 1) CK((h->legacy_qpd ? launch_qpd<10>(h, qa, B, cs) : launch_qpa<10>(h, qa, B, cs)));
     else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));
     else if (cls == 3) CK((launch_qpd<16>(h, qa, B, cs)));

@@ -183,6 +183,51 @@ def test_config3_shared_structure_groups_vs_oracle(planner):
         assert len(set(got.K[m])) == 1
 
 
+SHARED = dict(shared_kkt=1)  # K4a: shared-KKT tiles, multi-RHS solve on the FP64 tensor cores (qp_shared.cuh)
+
+
+@pytest.mark.parametrize("groups", [1, 8, 64])
+def test_shared_kkt_tiles_config3_vs_oracle(planner, groups):
+    """BASELINE configs[2] through the shared-KKT path: tiles of 8 scenarios of one structure group against ONE reduced-KKT
+    inverse (DMMA).  Same QP and same optimum as the reference: corridors bit-exact, decided solved / failed classes equal,
+    KKT-verified control points within 1e-5 / 1e-6 of the converged oracle.  (Iteration counts are not OSQP's: the tile
+    shares one scaling and one rho -- include/spectral.h, SpectralOptions::shared_kkt.)"""
+    batch = config3(512, groups=groups)
+    got = planner.solve("trp", batch, WEIGHTS_FILE, options=api.default_options(**SHARED))
+    ref, ref0 = H.oracle_pair("trp", batch, WEIGHTS_FILE)
+    H.assert_batch_parity(got, ref, "config3/shared/G%d" % groups, need_verified_frac=0.5, ref0=ref0, batch=batch, variant="trp",
+                          weights=WEIGHTS_FILE, min_iters_equal_frac=0.0, max_undecided_mismatch_frac=0.05)
+    # and against the per-scenario path: same classes wherever both hold a KKT proof, same optimum there
+    per = planner.solve("trp", batch, WEIGHTS_FILE)
+    both = got.verified() & per.verified()
+    assert both.sum() >= 40, both.sum()
+    for b in np.nonzero(both)[0]:
+        K = int(got.K[b])
+        assert H.close(got.ctrl[b, :12 * K], per.ctrl[b, :12 * K]), (b, H.maxdiff(got.ctrl[b, :12 * K], per.ctrl[b, :12 * K]))
+    # deterministic run to run (tiles are formed from the sorted (structure key, index) order)
+    again = planner.solve("trp", batch, WEIGHTS_FILE, options=api.default_options(**SHARED))
+    assert np.array_equal(got.ctrl, again.ctrl) and np.array_equal(got.iters, again.iters) and np.array_equal(got.status, again.status)
+
+
+def test_shared_kkt_mixed_structures_and_ragged_tiles(planner):
+    """The shared path on a batch that is NOT made of clean groups: config-2 scenarios (482 structures per 1024: tiles of 1-3
+    members, K > 8 members go to the per-scenario kernels) and per-scenario weights (the weights are part of the key)."""
+    batch = config2(384)
+    got = planner.solve("cub", batch, GOLDEN_W_CUB, options=api.default_options(**SHARED))
+    ref, ref0 = H.oracle_pair("cub", batch, GOLDEN_W_CUB)
+    # (with 1-3 members per tile the scaling / rho schedule differs from OSQP's on almost every scenario: the classes the
+    # reference does not pin itself -- slowly converging or infeasible-but-"inaccurate" at the cap -- flip more often here)
+    H.assert_batch_parity(got, ref, "config2/shared", need_verified_frac=0.5, ref0=ref0, batch=batch, variant="cub", weights=GOLDEN_W_CUB,
+                          min_iters_equal_frac=0.0, max_undecided_mismatch_frac=0.12)
+    w = np.tile(np.array(WEIGHTS_FILE), (64, 1))
+    w[::2, 0] = 20.0   # two weight vectors -> two keys per structure
+    b3 = config3(64, groups=1)
+    got = planner.solve("trp", b3, w, options=api.default_options(**SHARED))
+    ref, ref0 = H.oracle_pair("trp", b3, w)
+    H.assert_batch_parity(got, ref, "weights/shared", ref0=ref0, batch=b3, variant="trp", weights=w, min_iters_equal_frac=0.0,
+                          max_undecided_mismatch_frac=0.05)
+
+
 def test_mixed_variable_structure_vs_oracle(planner):
     """config 4 shape at test size: heterogeneous K, both variants."""
     for variant, batch in mixed_batches(640, seed=20230602):

@@ -152,5 +152,5 @@ extern "C" void emu_default_options(SpectralOptions *o) {
   o->max_iter = 5000; o->eps_abs = 1e-5; o->eps_rel = 1e-5; o->eps_prim_inf = 2.5e-5; o->rho = 0.1; o->sigma = 1e-6;
   o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
   o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
-  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3;
+  o->infeasibility_precheck = 0; o->precheck_margin = 1e-3; o->shared_kkt = 0;
 }

@@ -445,6 +445,121 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sweep5(args):
+    """--config 5: BASELINE configs[4], the 1 M-scenario sweep (config-4 generator, seed 20230603) STRONG-scaled over the
+    ranks, ending in the path's only exchange: spectral_sweep_argmin (NCCL all-gather of 16-byte records + winner broadcast
+    inside the C-ABI).  One step = one pass over all scenarios + the exchange."""
+    import torch
+    import torch.distributed as dist
+    from spectral_b200 import api, sweep_driver as sd
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.total
+    planner = api.SpectralPlanner(device=local, max_batch=sd.CHUNK, n_max=128, r_max=8, k_max=16)
+    ident = [api.SpectralPlanner.comm_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(ident, src=0)
+    planner.comm_init(world, rank, ident[0])
+    t0 = time.perf_counter()
+    shard = sd.upload_shard(total, rank, world, dev)
+    gen_s = time.perf_counter() - t0
+    n_local = (shard["g_hi"] - shard["g_lo"]) * sd.CHUNK
+    outs = planner.alloc_device_outputs(max(n_local, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    winner = None
+    for _ in range(max(1, args.warmup)):
+        winner = sd.run_sweep(planner, shard, outs)
+    barrier()
+    planner.get_work(reset=True)
+    l0 = planner.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        winner = sd.run_sweep(planner, shard, outs)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    work = planner.get_work(reset=True)
+    launches = planner.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = total * args.steps / (float(ms.item()) * 1e-3)
+    # every rank must hold the same winner
+    chk = torch.tensor([winner["cost"], float(winner["index"]), float(winner["rank"]), float(winner["K"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        ref = chk.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, chk), "ranks disagree on the winner"
+    # end to end: a bounded sample of this rank's chunks from page-locked host memory through solve_batch_async
+    names = ("s_bounds", "l_bounds", "ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars")
+    ns = min(8, len(shard["chunks"]))
+    from spectral_b200.wire import ScenarioBatch
+    host = []
+    for variant, N, R, delta, inp in shard["chunks"][:ns]:
+        host.append((variant, ScenarioBatch(N, R, delta, *[inp[k].cpu().numpy() for k in names])))
+    pls = [planner, api.SpectralPlanner(device=local, max_batch=sd.CHUNK, n_max=128, r_max=8, k_max=16)]
+    w_host = np.array(sd.WEIGHTS_FILE)
+    for rep in range(2):   # first repetition warms the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        for i, (variant, hb) in enumerate(host):
+            pl = pls[i % 2]
+            if getattr(pl, "_pending", None) is not None:
+                pl.wait()
+            pl.solve_async(variant, hb, w_host)
+        for pl in pls:
+            if getattr(pl, "_pending", None) is not None:
+                pl.wait()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * ns * sd.CHUNK / float(t_e.item()) if ns else 0.0
+    in_bytes = sum(a.nbytes for a in host[0][1].arrays()) if host else 0
+    if rank == 0:
+        fp64_peak = planner.measure_fp64_peak()
+        tf = work["admm_flops"] / (float(ms.item()) * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+                "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config5: %d-scenario sweep, config-4 generator (mixed trp+cub, K in [4,14], seed 20230603), contiguous "
+                                       "global-index shards over %d rank(s), one NCCL argmin exchange per pass (spectral_sweep_argmin)" % (total, world),
+                           "total_scenarios": total, "chunk": sd.CHUNK, "scenarios_this_rank": n_local,
+                           "l2": "inputs larger than L2: %.1f GB resident per rank" % (n_local * 8.1e3 / 1e9),
+                           "winner": {"cost": winner["cost"], "index": winner["index"], "rank": winner["rank"], "K": winner["K"]},
+                           "solved_fraction": work["solved"] / max(work["scenarios"], 1.0), "generation_s_untimed": gen_s,
+                           "mean_axis_iters": work["admm_iters"] / max(work["scenarios"], 1.0) / 2},
+                "roofline": {"kernel": "QP stage of rank 0 (k_qpa<8|10> + k_qpd<12|16>)", "bound": "fp64", "achieved": tf, "peak": fp64_peak,
+                             "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None, "traffic": None,
+                             "note": "rank 0's algorithmic flops (dense-operator count) over the whole timed pass, exchange included"},
+                "cpu_baseline": None,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes) * ns, "d2h_bytes_per_step": None,
+                        "sample": "the first %d chunks of every rank's shard from page-locked host buffers (spectral_solve_batch_async, 2 handles)" % ns},
+                "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,13 +567,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pool", type=int, default=0, help="distinct batches resident per rank (0: the workload's default)")
     ap.add_argument("--streams", type=int, default=0, help="steps in flight (one handle + CUDA stream each; 0: the workload's default)")
-    ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA)")
+    ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA); 5: configs[4] (1 M sweep, strong scaling)")
+    ap.add_argument("--total", type=int, default=1048576, help="config 5: scenarios in the sweep (multiple of 8192)")
     ap.add_argument("--no-shared", action="store_true", help="config 3 through the per-scenario kernels (A/B of the shared-KKT path)")
     ap.add_argument("--groups", type=int, default=8, help="config 3: number of shared-KKT groups (1, 8, 64)")
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 5:
+        run_sweep5(args)
     else:
         run_ours(args)
 

@@ -179,11 +179,42 @@ int spectral_solve_batch_device(spectral_handle_t *h, int variant, int B, int N,
                                 const SpectralInputs *dev_in, const SpectralOptions *opt,
                                 SpectralOutputs *dev_out, void *cuda_stream);
 
+/* Weight sweep: ONE scenario, B candidate weight vectors -- the batch form of the reference's tuning objective
+ * (src/trp_wrapper.py:56-97 run_btrapz: ten weights suggested in [0, 50] per trial, one find_traj call each).
+ * `in` holds one scenario (the [B] dimension of every array except `weights` is 1) and weights[B][10] (weights_stride is
+ * ignored).  The corridor stage (CorridorGeneration / CollisionCheck) runs once and is shared by all lanes: same A, same
+ * (l, u); P and q per weight vector.  Outputs are per lane, laid out as for spectral_solve_batch (segs / K repeated). */
+int spectral_solve_weights(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                           const SpectralInputs *host_in, const SpectralOptions *opt, SpectralOutputs *host_out);
+int spectral_solve_weights_device(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                  const SpectralInputs *dev_in, const SpectralOptions *opt, SpectralOutputs *dev_out, void *cuda_stream);
+
 /* Best trajectory of a sweep: (min a_cost, lowest index on ties) over B device-resident costs.
  * out_cost/out_index are DEVICE pointers (one double / one long long); index_offset is added to the
  * local index so shards can be compared across ranks. */
 int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,
                            double *out_cost_dev, long long *out_index_dev, void *cuda_stream);
+
+/* Multi-GPU sweep: scenarios are sharded over ranks (one handle = one GPU = one rank); the ONLY exchange is
+ * the best trajectory: local arg-min (k_argmin) -> NCCL all-gather of one 16-byte (cost, global index) record per rank ->
+ * NCCL broadcast of the winner's (K, segments, control points) from the rank that owns it.  Ties -> lowest global index;
+ * failed scenarios carry 1e11 (the reference's sentinel, trp_wrapper.cpp:199).  The library loads libnccl.so.2 at run time.
+ *   spectral_comm_unique_id  rank 0 makes the id (ncclGetUniqueId); the caller ships it to the other ranks by any means
+ *   spectral_comm_init       every rank, same id (ncclCommInitRank on the handle's device); nranks = 1 needs no NCCL
+ *   spectral_sweep_argmin    collective over all ranks; enqueued on cuda_stream, synchronises it, fills *winner on EVERY rank */
+typedef struct {
+  double cost;         /* a_cost of the best scenario (1e11: every scenario of the sweep failed) */
+  long long index;     /* its global index = index_offset of the owning rank + local index */
+  int rank;            /* the rank that owns it */
+  int K;
+  SpectralCube segs[32];
+  double ctrl[12 * 32]; /* s-axis control points [0, 6K), l-axis [6K, 12K) */
+} SpectralWinner;
+int spectral_comm_unique_id(unsigned char id[128]);
+int spectral_comm_init(spectral_handle_t *h, int nranks, int rank, const unsigned char id[128]);
+int spectral_comm_destroy(spectral_handle_t *h);
+int spectral_sweep_argmin(spectral_handle_t *h, int B_local, const SpectralOutputs *dev_out, long long index_offset,
+                          SpectralWinner *winner, void *cuda_stream);
 
 /* Number of kernel launches enqueued by this handle so far (for bench accounting). */
 long long spectral_launch_count(const spectral_handle_t *h);

@@ -69,6 +69,12 @@ class SpectralOptions(ctypes.Structure):
                 ("precheck_margin", ctypes.c_double), ("shared_kkt", ctypes.c_int)]
 
 
+class SpectralWinner(ctypes.Structure):
+    """SpectralWinner of include/spectral.h: the best trajectory of a (multi-GPU) sweep."""
+    _fields_ = [("cost", ctypes.c_double), ("index", ctypes.c_longlong), ("rank", ctypes.c_int), ("K", ctypes.c_int),
+                ("segs", ctypes.c_ubyte * (32 * 112)), ("ctrl", ctypes.c_double * (12 * 32))]
+
+
 class Params(ctypes.Structure):
     """struct Params of include/btrapz/py_cpp_.h:6-21 == class Params of src/trp_wrapper.py:19-32."""
     _fields_ = [("s_acc_weight", ctypes.c_double), ("s_jerk_weight", ctypes.c_double),
@@ -107,6 +113,8 @@ def load_library() -> ctypes.CDLL:
         fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                        ctypes.POINTER(SpectralInputs), ctypes.POINTER(SpectralOptions), ctypes.POINTER(SpectralOutputs)]
     lib.spectral_solve_batch_device.argtypes = lib.spectral_solve_batch.argtypes + [ctypes.c_void_p]
+    lib.spectral_solve_weights.argtypes = lib.spectral_solve_batch.argtypes
+    lib.spectral_solve_weights_device.argtypes = lib.spectral_solve_batch_device.argtypes
     lib.spectral_argmin_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.spectral_launch_count.argtypes = [ctypes.c_void_p]
@@ -116,6 +124,9 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), _ip]
     lib.spectral_get_work.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int]
     lib.spectral_get_class_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    lib.spectral_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ubyte)]
+    lib.spectral_comm_unique_id.argtypes = [ctypes.POINTER(ctypes.c_ubyte)]
+    lib.spectral_sweep_argmin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
     return lib
 
@@ -214,6 +225,30 @@ class SpectralPlanner:
                                                    float(batch.delta_t), ctypes.byref(inp),
                                                    ctypes.byref(options) if options is not None else None,
                                                    ctypes.byref(out)))
+        return res
+
+    def solve_weights(self, variant, scenario: ScenarioBatch, weights, options: Optional[SpectralOptions] = None,
+                      samples_cap: int = 0) -> BatchResult:
+        """Weight sweep (the batch form of trp_wrapper.py:56-97 run_btrapz): ONE scenario (a ScenarioBatch of 1) against
+        B weight vectors [B, 10]; the corridor stage runs once on the device and is shared by all lanes."""
+        if scenario.batch != 1:
+            raise ValueError("solve_weights takes exactly one scenario")
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+        if w.ndim != 2 or w.shape[1] != 10:
+            raise ValueError("weights must have shape (B, 10)")
+        B = w.shape[0]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in scenario.arrays()]
+        inp = SpectralInputs(*[_d(a) for a in arrs], _d(w), 1)
+        km = self.k_max
+        res = BatchResult(np.zeros(B, np.int32), np.zeros((B, km), CUBE_DTYPE), np.zeros((B, 12 * km)), np.zeros(B),
+                          np.zeros(B), np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32),
+                          np.zeros(B, np.int32), np.zeros((B, samples_cap, 6)) if samples_cap > 0 else None, None)
+        out = SpectralOutputs(_i(res.K), res.segs.ctypes.data_as(ctypes.c_void_p), _d(res.ctrl), _d(res.obj),
+                              _d(res.a_cost), _i(res.status), _i(res.iters), _i(res.flags), _i(res.npts),
+                              _d(res.samples), samples_cap, None)
+        self._check(self._lib.spectral_solve_weights(self._h, VARIANT_ID[variant], B, scenario.n_knots, scenario.n_regions,
+                                                     float(scenario.delta_t), ctypes.byref(inp),
+                                                     ctypes.byref(options) if options is not None else None, ctypes.byref(out)))
         return res
 
     # ---- pipelined host path: page-locked buffers owned by the planner, one batch in flight per planner
@@ -331,6 +366,38 @@ class SpectralPlanner:
         self._check(self._lib.spectral_argmin_device(self._h, int(a_cost.numel()), ctypes.c_void_p(a_cost.data_ptr()),
                                                      int(index_offset), ctypes.c_void_p(out_cost.data_ptr()),
                                                      ctypes.c_void_p(out_index.data_ptr()), ctypes.c_void_p(stream)))
+
+    # ---- multi-GPU exchange through the C-ABI (NCCL inside libspectral.so)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (ctypes.c_ubyte * 128)()
+        if load_library().spectral_comm_unique_id(buf) != 0:
+            raise RuntimeError("spectral_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: Optional[bytes]) -> None:
+        buf = (ctypes.c_ubyte * 128)(*unique_id) if unique_id is not None else None
+        self._check(self._lib.spectral_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def sweep_argmin(self, outputs: dict, index_offset: int, B: Optional[int] = None, stream: Optional[int] = None) -> dict:
+        """Collective over all ranks of the communicator: this rank's shard results (device outputs of solve_device)
+        -> the sweep's best trajectory on every rank (spectral_sweep_argmin)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        B = int(outputs["a_cost"].numel()) if B is None else int(B)
+        out = SpectralOutputs()
+        out.K = ctypes.cast(ctypes.c_void_p(outputs["K"].data_ptr()), _ip)
+        out.segs = outputs["segs"].data_ptr()
+        out.ctrl = ctypes.cast(ctypes.c_void_p(outputs["ctrl"].data_ptr()), _dp)
+        out.a_cost = ctypes.cast(ctypes.c_void_p(outputs["a_cost"].data_ptr()), _dp)
+        w = SpectralWinner()
+        self._check(self._lib.spectral_sweep_argmin(self._h, B, ctypes.byref(out), int(index_offset), ctypes.byref(w),
+                                                    ctypes.c_void_p(stream)))
+        K = int(w.K)
+        segs = np.frombuffer(bytes(w.segs), dtype=CUBE_DTYPE)[:max(K, 0)].copy()
+        return dict(cost=float(w.cost), index=int(w.index), rank=int(w.rank), K=K, segs=segs,
+                    ctrl=np.array(w.ctrl[:12 * max(K, 0)], dtype=np.float64))
 
     def launch_count(self) -> int:
         return int(self._lib.spectral_launch_count(self._h))

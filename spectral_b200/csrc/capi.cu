@@ -5,6 +5,8 @@
 // SPECTRAL_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed at run time (spectral_comm_*), libspectral.so has no link dependency on it
 
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +114,15 @@ __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a
                        else asm volatile("bar.sync 2, %0;" ::"n"(QpdLayout<KC>::TA) : "memory");
                      });
   }
+}
+
+// weight sweep: the corridor stage ran for scenario 0 only; every lane gets its (K, segments, corridor status)
+__global__ void k_broadcast_corridor(int *K, SpectralCube *segs, int *cstatus, int k_max, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || b == 0) return;
+  K[b] = K[0]; cstatus[b] = cstatus[0];
+  const int n = K[0] < k_max ? K[0] : k_max;
+  for (int k = 0; k < n; k++) segs[(size_t)b * k_max + k] = segs[k];
 }
 
 // ------------------------------------------------------------------ shared-KKT path (qp_shared.cuh)
@@ -312,6 +323,11 @@ struct spectral_handle {
   double *qs_lu = nullptr, *qs_qv = nullptr, *qs_w = nullptr, *qs_x = nullptr, *qs_fs = nullptr;
   void *qs_cub = nullptr;
   size_t qs_cub_bytes = 0;
+  // multi-GPU exchange (spectral_comm_* / spectral_sweep_argmin)
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  double *xg_rec = nullptr;        // [1 + nranks] (cost, index) records, 16 bytes each
+  unsigned char *xg_pay = nullptr; // winner payload
   int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
@@ -384,6 +400,9 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
 extern "C" int spectral_destroy(spectral_handle_t *h) {
   if (!h) return SPECTRAL_ERR_INVALID;
   cudaSetDevice(h->device);
+  if (h->comm) spectral_comm_destroy(h);
+  if (h->xg_rec) cudaFree(h->xg_rec);
+  if (h->xg_pay) cudaFree(h->xg_pay);
   void *qsb[] = {h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, h->qs_tmp, h->qs_tile, h->qs_leader, h->qs_misc, h->qs_st, h->qs_blk, h->qs_lu,
                  h->qs_qv, h->qs_w, h->qs_x, h->qs_cub, h->qs_fs};
   for (void *p : qsb) if (p) cudaFree(p);
@@ -493,7 +512,7 @@ static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, 
   int *tile_start = h->qs_tile, *tile_count = h->qs_tile + Bm;
   const int nb = (B + 255) / 256;
   CK(cudaMemsetAsync(h->qs_misc, 0, 8, st));
-  k_qps_keys<<<nb, 256, 0, st>>>(cstatus, qa.K, qa.segs, h->k_max, in->weights, in->weights_stride, B, h->qs_keys, h->qs_ids, h->qs_leader);
+  k_qps_keys<<<nb, 256, 0, st>>>(cstatus, qa.K, qa.segs, h->k_max, qa.weights, qa.wstride, B, h->qs_keys, h->qs_ids, h->qs_leader);
   size_t tb = h->qs_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(h->qs_cub, tb, h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, B, 0, 64, st));
   k_qps_heads<<<nb, 256, 0, st>>>(h->qs_keys2, B, head);
@@ -537,9 +556,23 @@ static cudaError_t launch_qp(spectral_handle *h, const QpArgs &qa, int B, cudaSt
   return cudaGetLastError();
 }
 
+static int solve_device_impl(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t, const SpectralInputs *in,
+                             const SpectralOptions *opt_in, SpectralOutputs *out, void *cuda_stream, int sweep);
+
 extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
                                            const SpectralInputs *in, const SpectralOptions *opt_in,
                                            SpectralOutputs *out, void *cuda_stream) {
+  return solve_device_impl(h, variant, B, N, R, delta_t, in, opt_in, out, cuda_stream, 0);
+}
+extern "C" int spectral_solve_weights_device(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                             const SpectralInputs *in, const SpectralOptions *opt_in,
+                                             SpectralOutputs *out, void *cuda_stream) {
+  return solve_device_impl(h, variant, B, N, R, delta_t, in, opt_in, out, cuda_stream, 1);
+}
+
+// sweep = 1: `in` holds ONE scenario and B weight vectors (weight sweep): corridor stage once, QP per lane
+static int solve_device_impl(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t, const SpectralInputs *in,
+                             const SpectralOptions *opt_in, SpectralOutputs *out, void *cuda_stream, int sweep) {
   if (!h || !in || !out) return SPECTRAL_ERR_INVALID;
   if (B <= 0 || B > h->max_batch || N < 3 || N > h->n_max || R < 1 || R > h->r_max)
     return fail(h, SPECTRAL_ERR_CAPACITY, "batch shape exceeds the handle's capacity");
@@ -555,17 +588,22 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K3a: weight tables
-  const int W = in->weights_stride ? B : 1;
+  const int wstride = sweep ? 1 : in->weights_stride;
+  const int W = wstride ? B : 1;
   k_tables<<<(2 * W + 127) / 128, 128, 0, st>>>(in->weights, h->mqm, W);
   h->launches++;
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // K1 + K2: corridors
-  CorridorArgs ca{B, N, R, variant, h->k_max, delta_t, in->s_bounds, in->l_bounds, in->s_ref, in->l_ref, out->segs, out->K, h->cstatus};
+  CorridorArgs ca{sweep ? 1 : B, N, R, variant, h->k_max, delta_t, in->s_bounds, in->l_bounds, in->s_ref, in->l_ref, out->segs, out->K, h->cstatus};
   if (spectral_corridor_prepare(N, R, &h->corridor_smem) != 0) return fail(h, SPECTRAL_ERR_CUDA, "corridor kernel: shared memory opt-in failed");
   spectral_launch_corridor(ca, st);
   h->launches++;
   CK(cudaGetLastError());
+  if (sweep && B > 1) {
+    k_broadcast_corridor<<<(B + 255) / 256, 256, 0, st>>>(out->K, out->segs, h->cstatus, h->k_max, B);
+    h->launches++;
+  }
   if (tm) CK(cudaEventRecord(ev[evi++], st));
 
   // classification by segment count -> lane class lists
@@ -579,7 +617,7 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   QpArgs qa;
   qa.N = N; qa.k_max = h->k_max; qa.variant = variant; qa.delta = delta_t;
   qa.ds_bounds = in->ds_bounds; qa.dl_bounds = in->dl_bounds; qa.s_ref = in->s_ref; qa.l_ref = in->l_ref;
-  qa.init = in->init; qa.scalars = in->scalars; qa.weights = in->weights; qa.wstride = in->weights_stride;
+  qa.init = in->init; qa.scalars = in->scalars; qa.weights = in->weights; qa.wstride = wstride; qa.in_stride = sweep ? 0 : 1;
   qa.mqm = h->mqm; qa.segs = out->segs; qa.K = out->K;
   qa.opt.max_iter = opt.max_iter; qa.opt.scaling = opt.scaling; qa.opt.check_every = opt.check_termination;
   qa.opt.adapt_every = opt.adaptive_rho_interval; qa.opt.polish = opt.polish; qa.opt.polish_refine = opt.polish_refine_iter;
@@ -616,7 +654,7 @@ extern "C" int spectral_solve_batch_device(spectral_handle_t *h, int variant, in
   // K5: sampling + cost + status merge
   FinalArgs fa;
   fa.B = B; fa.N = N; fa.k_max = h->k_max; fa.variant = variant; fa.delta = delta_t; fa.s_ref = in->s_ref; fa.l_ref = in->l_ref;
-  fa.init = in->init; fa.weights = in->weights; fa.wstride = in->weights_stride; fa.segs = out->segs; fa.K = out->K;
+  fa.init = in->init; fa.weights = in->weights; fa.wstride = wstride; fa.in_stride = sweep ? 0 : 1; fa.segs = out->segs; fa.K = out->K;
   fa.cstatus = h->cstatus; fa.axis_status = h->axis_status; fa.axis_iters = h->axis_iters; fa.axis_polished = h->axis_polished;
   fa.axis_obj = h->axis_obj; fa.ctrl = out->ctrl; fa.obj = out->obj; fa.a_cost = out->a_cost; fa.samples = out->samples;
   fa.status = out->status; fa.iters = out->iters; fa.flags = out->flags; fa.npts = out->npts; fa.samples_cap = out->samples_cap;
@@ -645,8 +683,20 @@ static int ensure(spectral_handle *h, T **p, size_t *cur, size_t need) {
   return SPECTRAL_SUCCESS;
 }
 
+static int solve_async_impl(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t, const SpectralInputs *hin,
+                            const SpectralOptions *opt, SpectralOutputs *hout, int sweep);
 extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
                                           const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
+  return solve_async_impl(h, variant, B, N, R, delta_t, hin, opt, hout, 0);
+}
+extern "C" int spectral_solve_weights(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t,
+                                      const SpectralInputs *hin, const SpectralOptions *opt, SpectralOutputs *hout) {
+  const int rc = solve_async_impl(h, variant, B, N, R, delta_t, hin, opt, hout, 1);
+  if (rc) return rc;
+  return spectral_wait(h);
+}
+static int solve_async_impl(spectral_handle_t *h, int variant, int B, int N, int R, double delta_t, const SpectralInputs *hin,
+                            const SpectralOptions *opt, SpectralOutputs *hout, int sweep) {
   if (!h || !hin || !hout) return SPECTRAL_ERR_INVALID;
   if (B <= 0 || B > h->max_batch || N < 3 || N > h->n_max || R < 1 || R > h->r_max)
     return fail(h, SPECTRAL_ERR_CAPACITY, "batch shape exceeds the handle's capacity");
@@ -656,8 +706,9 @@ extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t b = (size_t)B, n = (size_t)N, r = (size_t)R, km = (size_t)h->k_max;
-  const size_t in_bytes[9] = {b * r * n * 16, b * r * n * 16, b * n * 16, b * n * 16, b * n * 8, b * n * 8, b * 48, b * 80,
-                              (hin->weights_stride ? b : 1) * 80};
+  const size_t bs = sweep ? 1 : b;  // scenarios uploaded
+  const size_t in_bytes[9] = {bs * r * n * 16, bs * r * n * 16, bs * n * 16, bs * n * 16, bs * n * 8, bs * n * 8, bs * 48, bs * 80,
+                              ((sweep || hin->weights_stride) ? b : 1) * 80};
   const double *src[9] = {hin->s_bounds, hin->l_bounds, hin->ds_bounds, hin->dl_bounds, hin->s_ref, hin->l_ref, hin->init,
                           hin->scalars, hin->weights};
   for (int i = 0; i < 9; i++) {
@@ -691,7 +742,7 @@ extern "C" int spectral_solve_batch_async(spectral_handle_t *h, int variant, int
   CK(cudaMemsetAsync(h->d_ctrl, 0, b * 12 * km * 8, st));
   CK(cudaMemsetAsync(h->d_segs, 0, b * km * sizeof(SpectralCube), st));
   if (hout->samples) CK(cudaMemsetAsync(h->d_samples, 0, b * (size_t)hout->samples_cap * 48, st));
-  int rc = spectral_solve_batch_device(h, variant, B, N, R, delta_t, &din, opt, &dout, st);
+  int rc = solve_device_impl(h, variant, B, N, R, delta_t, &din, opt, &dout, st, sweep);
   if (rc) return rc;
 #define D2H(dst, srcp, bytes) do { if (dst) CK(cudaMemcpyAsync((dst), (srcp), (bytes), cudaMemcpyDeviceToHost, st)); } while (0)
   D2H(hout->K, h->d_K, b * 4); D2H(hout->status, h->d_status, b * 4); D2H(hout->iters, h->d_iters, b * 4);
@@ -739,6 +790,148 @@ extern "C" int spectral_argmin_device(spectral_handle_t *h, int B, const double 
   k_argmin<<<blocks, 256, 0, st>>>(a_cost_dev, B, index_offset, h->partial, h->ticket, out_cost_dev, out_index_dev);
   h->launches++;
   CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
+// ------------------------------------------------------------------ multi-GPU best-trajectory exchange (NCCL)
+namespace {
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // the soname first: in a process that already holds an NCCL (e.g. torch's bundled one) this resolves to THAT copy
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+      api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+      api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Broadcast) api.lib = nullptr;
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+struct WinnerRec { double cost; long long idx; };
+// payload of a winner: K, then the segments, then the control points
+constexpr size_t kPayBytes = 16 + 32 * sizeof(SpectralCube) + 12 * 32 * 8;
+__global__ void k_pack_record(const double *cost, const long long *idx, WinnerRec *rec) { rec->cost = *cost; rec->idx = *idx; }
+__global__ void k_pick_winner(const WinnerRec *all, int nranks, WinnerRec *win, int *win_rank) {
+  ArgminPair best{1.0e300, 0x7fffffffffffffffLL};
+  int br = 0;
+  for (int r = 0; r < nranks; r++) {
+    const ArgminPair o{all[r].cost, all[r].idx};
+    const ArgminPair nb = argmin_better(best, o);
+    if (nb.idx != best.idx || nb.cost != best.cost) br = r;
+    best = nb;
+  }
+  win->cost = best.cost; win->idx = best.idx; *win_rank = br;
+}
+__global__ void k_pack_winner(const WinnerRec *win, long long offset, int B, int k_max, const int *K, const SpectralCube *segs, const double *ctrl,
+                              unsigned char *pay) {
+  const long long loc = win->idx - offset;
+  if (loc < 0 || loc >= B) return;  // not this rank's scenario
+  int *hdr = (int *)pay;
+  const int Kw = K[loc];
+  if (threadIdx.x == 0) { hdr[0] = Kw; hdr[1] = k_max; hdr[2] = 0; hdr[3] = 0; }
+  SpectralCube *ps = (SpectralCube *)(pay + 16);
+  double *pc = (double *)(pay + 16 + 32 * sizeof(SpectralCube));
+  for (int k = threadIdx.x; k < 32; k += blockDim.x)
+    if (k < Kw && k < k_max) ps[k] = segs[(size_t)loc * k_max + k];
+  for (int j = threadIdx.x; j < 12 * 32; j += blockDim.x) pc[j] = (j < 12 * Kw && j < 12 * k_max) ? ctrl[(size_t)loc * 12 * k_max + j] : 0.0;
+}
+}  // namespace
+
+extern "C" int spectral_comm_unique_id(unsigned char id[128]) {
+  if (!id) return SPECTRAL_ERR_INVALID;
+  NcclApi *n = nccl_api();
+  if (!n) return SPECTRAL_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+  ncclUniqueId u;
+  if (n->GetUniqueId(&u) != ncclSuccess) return SPECTRAL_ERR_CUDA;
+  memcpy(id, &u, 128);
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_comm_init(spectral_handle_t *h, int nranks, int rank, const unsigned char id[128]) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (h->comm) spectral_comm_destroy(h);
+  h->nranks = nranks; h->rank = rank;
+  if (h->xg_rec) { cudaFree(h->xg_rec); h->xg_rec = nullptr; }
+  CK(cudaMalloc(&h->xg_rec, (size_t)(4 + nranks) * sizeof(WinnerRec)));
+  if (!h->xg_pay) CK(cudaMalloc(&h->xg_pay, kPayBytes));
+  if (nranks == 1) return SPECTRAL_SUCCESS;
+  NcclApi *n = nccl_api();
+  if (!n || !id) return fail(h, SPECTRAL_ERR_CUDA, "NCCL is not available (libnccl.so.2 could not be loaded)");
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  const ncclResult_t r = n->CommInitRank(&h->comm, nranks, u, rank);
+  if (r != ncclSuccess) return fail(h, SPECTRAL_ERR_CUDA, std::string("ncclCommInitRank: ") + (n->GetErrorString ? n->GetErrorString(r) : "error"));
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_comm_destroy(spectral_handle_t *h) {
+  if (!h) return SPECTRAL_ERR_INVALID;
+  if (h->comm) {
+    NcclApi *n = nccl_api();
+    if (n) n->CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->nranks = 1; h->rank = 0;
+  return SPECTRAL_SUCCESS;
+}
+
+extern "C" int spectral_sweep_argmin(spectral_handle_t *h, int B_local, const SpectralOutputs *dev_out, long long index_offset,
+                                     SpectralWinner *winner, void *cuda_stream) {
+  if (!h || !dev_out || !winner || B_local <= 0 || !dev_out->a_cost || !dev_out->K || !dev_out->segs || !dev_out->ctrl) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (!h->xg_rec) { const int rc = spectral_comm_init(h, 1, 0, nullptr); if (rc) return rc; }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  WinnerRec *rec = (WinnerRec *)h->xg_rec;          // [0] local, [1] winner, [2 ..] gathered, [2 + nranks] scratch (cost, idx)
+  WinnerRec *win = rec + 1, *all = rec + 2;
+  double *tmp_cost = (double *)(rec + 2 + h->nranks);
+  long long *tmp_idx = (long long *)(tmp_cost + 1);
+  int *win_rank = (int *)(rec + 3 + h->nranks);
+  int rc = spectral_argmin_device(h, B_local, dev_out->a_cost, index_offset, tmp_cost, tmp_idx, st);
+  if (rc) return rc;
+  k_pack_record<<<1, 1, 0, st>>>(tmp_cost, tmp_idx, rec);
+  NcclApi *n = h->nranks > 1 ? nccl_api() : nullptr;
+  if (h->nranks > 1) {
+    if (!n || !h->comm) return fail(h, SPECTRAL_ERR_INVALID, "spectral_comm_init has not been called on this handle");
+    if (n->AllGather(rec, all, sizeof(WinnerRec), ncclUint8, h->comm, st) != ncclSuccess) return fail(h, SPECTRAL_ERR_CUDA, "ncclAllGather");
+  } else {
+    CK(cudaMemcpyAsync(all, rec, sizeof(WinnerRec), cudaMemcpyDeviceToDevice, st));
+  }
+  k_pick_winner<<<1, 1, 0, st>>>(all, h->nranks, win, win_rank);
+  k_pack_winner<<<1, 128, 0, st>>>(win, index_offset, B_local, h->k_max, dev_out->K, dev_out->segs, dev_out->ctrl, h->xg_pay);
+  h->launches += 3;
+  WinnerRec hw;
+  int hr = 0;
+  CK(cudaMemcpyAsync(&hw, win, sizeof(WinnerRec), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hr, win_rank, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h->nranks > 1 && n->Broadcast(h->xg_pay, h->xg_pay, kPayBytes, ncclUint8, hr, h->comm, st) != ncclSuccess)
+    return fail(h, SPECTRAL_ERR_CUDA, "ncclBroadcast");
+  static unsigned char hostpay[kPayBytes];  // (a handle is not thread-safe; one exchange at a time per process)
+  CK(cudaMemcpyAsync(hostpay, h->xg_pay, kPayBytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memset(winner, 0, sizeof(*winner));
+  winner->cost = hw.cost; winner->index = hw.idx; winner->rank = hr;
+  const int *hdr = (const int *)hostpay;
+  winner->K = hdr[0];
+  memcpy(winner->segs, hostpay + 16, 32 * sizeof(SpectralCube));
+  memcpy(winner->ctrl, hostpay + 16 + 32 * sizeof(SpectralCube), 12 * 32 * 8);
   return SPECTRAL_SUCCESS;
 }
 

@@ -11,6 +11,7 @@ struct FinalArgs {
   double delta;
   const double *s_ref, *l_ref, *init, *weights;
   int wstride;
+  int in_stride;  // 1: one input scenario per lane; 0: every lane reads scenario 0 (weight sweep, spectral_solve_weights)
   const SpectralCube *segs;
   const int *K, *cstatus, *axis_status, *axis_iters, *axis_polished;
   const double *axis_obj, *ctrl;
@@ -63,8 +64,9 @@ SP_DEV void finalize_body(const FinalArgs &a, int b) {
     const SpectralCube *segs = a.segs + (size_t)b * a.k_max;
     const double *ctrl = a.ctrl + (size_t)b * 12 * a.k_max;
     const double *wv = a.weights + (size_t)(a.wstride ? b : 0) * 10;
-    const double *sref = a.s_ref + (size_t)b * N, *lref = a.l_ref + (size_t)b * N;
-    const double *ini = a.init + 6 * (size_t)b;
+    const size_t bi = (size_t)b * a.in_stride;
+    const double *sref = a.s_ref + bi * N, *lref = a.l_ref + bi * N;
+    const double *ini = a.init + 6 * bi;
     double *smp = a.samples ? a.samples + (size_t)b * a.samples_cap * 6 : nullptr;
     int num_of_points = 1;  // solve_3d.h:114
     for (int k = 0; k < K; k++) num_of_points = (int)((double)num_of_points + segs[k].t / delta);  // int += double (:1281)

@@ -49,6 +49,7 @@ struct QpArgs {
   double delta;
   const double *ds_bounds, *dl_bounds, *s_ref, *l_ref, *init, *scalars, *weights;
   int wstride;
+  int in_stride;     // 1: one input scenario per lane; 0: every lane reads scenario 0 (weight sweep)
   const double *mqm;  // [W][2 axes][4][21] packed lower triangle of M' pQp_d M
   const SpectralCube *segs;
   const int *K;
@@ -490,10 +491,11 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
   double tp = sp_shfl_up(t, 1, LPA), tn = sp_shfl_down(t, 1, LPA);
   if (first) tp = 1.0;
   if (last || !active) tn = 1.0;
-  const double *sc = a.scalars + 10 * (size_t)b;
+  const size_t bi = (size_t)b * a.in_stride;  // input scenario of this lane
+  const double *sc = a.scalars + 10 * bi;
   const double *wv = a.weights + (size_t)(a.wstride ? b : 0) * 10;
-  const double *ref = (axis == 0 ? a.s_ref : a.l_ref) + (size_t)b * N;
-  const double *ini = a.init + 6 * (size_t)b + 3 * axis;
+  const double *ref = (axis == 0 ? a.s_ref : a.l_ref) + bi * N;
+  const double *ini = a.init + 6 * bi + 3 * axis;
   const double invm[6] = {SP_INVM1_0, SP_INVM1_1, SP_INVM1_2, SP_INVM1_3, SP_INVM1_4, SP_INVM1_5};
   double lo[QP_ROWS], hi[QP_ROWS];
   // containment rows (solve_3d.cc:823-832, :961-977; cuboid_3d.cc:677-697, :826-827)
@@ -532,7 +534,7 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
   if (axis == 0) {
     double d_lo = 0.0, d_hi = 1000.0, dd_lo = -1000.0, dd_hi = 1000.0;
     if (active) {
-      const double *dsb = a.ds_bounds + (size_t)b * N * 2;
+      const double *dsb = a.ds_bounds + bi * N * 2;
       for (int i = cube.beg_t; i <= cube.end_t; i++) {
         const double blo = dsb[2 * i], bhi = dsb[2 * i + 1];
         d_lo = (blo < d_lo) ? d_lo : blo;  // std::max(bound, cur)
@@ -548,7 +550,7 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
 #pragma unroll
     for (int i = 0; i < 3; i++) { lo[15 + i] = rn_mul(rn_mul(sc[4], t), t); hi[15 + i] = rn_mul(rn_mul(sc[5], t), t); }
   } else {
-    const double *dlb = a.dl_bounds + (size_t)b * N * 2;
+    const double *dlb = a.dl_bounds + bi * N * 2;
 #pragma unroll
     for (int i = 0; i < 5; i++) { lo[6 + i] = dlb[2 * i]; hi[6 + i] = dlb[2 * i + 1]; }  // dy_bounds_[i]: control index (:1003)
 #pragma unroll

@@ -262,6 +262,26 @@ def test_many_segments_class_vs_oracle(planner):
                           got0=_raw(planner, "trp", batch, WEIGHTS_FILE), max_undecided_mismatch_frac=0.05)
 
 
+def test_weight_sweep_entry(planner):
+    """spectral_solve_weights: one scenario, B weight vectors drawn like the reference's tuning objective (ten
+    trial.suggest_float(.., 0, 50), trp_wrapper.py:69-80).  The corridor stage runs once; every lane must equal the same
+    scenario replicated B times through the batch entry bit for bit, and the batch must meet the oracle's parity bars."""
+    B = 192
+    one = ScenarioBatch.from_scenarios([load_fixture("c1")])
+    w = np.random.default_rng(20230604).uniform(0.0, 50.0, (B, 10))
+    w[0] = GOLDEN_W_TRP
+    got = planner.solve_weights("trp", one, w)
+    rep = ScenarioBatch(one.n_knots, one.n_regions, one.delta_t, *[np.repeat(a, B, axis=0) for a in one.arrays()])
+    same = planner.solve("trp", rep, w)
+    for f in ("K", "status", "iters", "flags", "npts", "ctrl", "obj", "a_cost"):
+        assert np.array_equal(getattr(got, f), getattr(same, f)), f
+    assert got.segs.tobytes() == same.segs.tobytes()
+    ref, ref0 = H.oracle_pair("trp", rep, w)
+    H.assert_batch_parity(got, ref, "weight-sweep", ref0=ref0, batch=rep, variant="trp", weights=w,
+                          got0=planner.solve_weights("trp", one, w, options=api.default_options(**NO_POLISH)))
+    assert np.argmin(got.a_cost) == np.argmin(same.a_cost)
+
+
 def test_edge_cases(planner):
     # B = 1, minimal horizon that still yields a corridor, R = 1
     sc = load_fixture("c2")
@@ -346,6 +366,37 @@ def test_device_resident_path_and_argmin(planner):
     assert np.array_equal(outs["a_cost"].cpu().numpy(), host.a_cost)
     j = int(np.argmin(host.a_cost))  # numpy argmin returns the first minimum = lowest index on ties
     assert int(best_idx.item()) == 1000 + j and best_cost.item() == host.a_cost[j]
+
+
+def test_sweep_argmin_through_the_c_abi():
+    """Config-5 path at test size, one rank: spectral_sweep_argmin (k_argmin -> record -> winner payload) returns the arg-min
+    scenario's K / segments / control points; cutting the same sweep into two contiguous shards (what two ranks would run)
+    gives the same winner -- it does not depend on the number of ranks (ties -> lowest global index)."""
+    import torch
+    from spectral_b200 import sweep_driver as sd
+    dev = torch.device("cuda", 0)
+    pl = api.SpectralPlanner(device=0, max_batch=sd.CHUNK, n_max=128, r_max=8, k_max=16)
+    pl.comm_init(1, 0, None)
+    total = 4 * sd.CHUNK
+    shard = sd.upload_shard(total, 0, 1, dev)
+    outs = pl.alloc_device_outputs(total)
+    win = sd.run_sweep(pl, shard, outs)
+    cost = outs["a_cost"].cpu().numpy()
+    j = int(np.argmin(cost))
+    assert win["index"] == j and win["cost"] == cost[j] and win["rank"] == 0 and cost[j] < api.FAIL_COST
+    K = int(outs["K"][j].item())
+    assert win["K"] == K
+    assert np.array_equal(win["ctrl"], outs["ctrl"][j].cpu().numpy()[:12 * K])
+    segs = outs["segs"][j].cpu().numpy().view(api.CUBE_DTYPE)[:K]
+    assert win["segs"].tobytes() == segs.tobytes()
+    halves = []
+    for r in range(2):
+        sh = sd.upload_shard(total, r, 2, dev)
+        o = pl.alloc_device_outputs((sh["g_hi"] - sh["g_lo"]) * sd.CHUNK)
+        halves.append(sd.run_sweep(pl, sh, o))
+    best = min(halves, key=lambda w: (w["cost"], w["index"]))
+    assert best["index"] == win["index"] and best["cost"] == win["cost"] and np.array_equal(best["ctrl"], win["ctrl"])
+    pl.close()
 
 
 def test_infeasibility_precheck_is_sound(planner):

@@ -89,7 +89,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
     QpArgs qa;
     qa.N = N; qa.k_max = k_max; qa.variant = variant; qa.delta = delta;
     qa.ds_bounds = ds_bounds; qa.dl_bounds = dl_bounds; qa.s_ref = s_ref; qa.l_ref = l_ref; qa.init = init;
-    qa.scalars = scalars; qa.weights = weights; qa.wstride = wstride; qa.mqm = mqm.data(); qa.segs = segs; qa.K = K;
+    qa.scalars = scalars; qa.weights = weights; qa.wstride = wstride; qa.in_stride = 1; qa.mqm = mqm.data(); qa.segs = segs; qa.K = K;
     qa.list = list[cls].data(); qa.count = &cnt; qa.next = nullptr; qa.opt = od; qa.ctrl = ctrl; qa.axis_status = axis_status.data();
     qa.axis_iters = axis_iters.data(); qa.axis_polished = axis_pol.data(); qa.axis_obj = axis_obj.data(); qa.lu = lu;
     if (cls <= 3 && !force_lanes) {
@@ -140,7 +140,7 @@ extern "C" int emu_solve_batch(int variant, int B, int N, int R, double delta, c
   // ---- finalize
   FinalArgs fa;
   fa.B = B; fa.N = N; fa.k_max = k_max; fa.variant = variant; fa.delta = delta; fa.s_ref = s_ref; fa.l_ref = l_ref;
-  fa.init = init; fa.weights = weights; fa.wstride = wstride; fa.segs = segs; fa.K = K; fa.cstatus = cstatus.data();
+  fa.init = init; fa.weights = weights; fa.wstride = wstride; fa.in_stride = 1; fa.segs = segs; fa.K = K; fa.cstatus = cstatus.data();
   fa.axis_status = axis_status.data(); fa.axis_iters = axis_iters.data(); fa.axis_polished = axis_pol.data();
   fa.axis_obj = axis_obj.data(); fa.ctrl = ctrl; fa.obj = obj; fa.a_cost = a_cost; fa.samples = samples;
   fa.status = status; fa.iters = iters; fa.flags = flags; fa.npts = npts; fa.samples_cap = samples_cap;

@@ -195,6 +195,19 @@ int spectral_solve_weights_device(spectral_handle_t *h, int variant, int B, int 
 int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,
                            double *out_cost_dev, long long *out_index_dev, void *cuda_stream);
 
+/* Downstream of the path, device buffers, enqueued on cuda_stream:
+ * spectral_ego_states_device         run_ego() of src/cart_frenet.py:1126-1221: samples [B][cap][6] (the `samples` output:
+ *                                    s, ds, dds, l, dl, ddl) + npts [B] -> states [B][cap][4] = (position along the road,
+ *                                    lateral position, speed with ds floored at 5.0, heading = round(atan2(dl, ds), 2) of the
+ *                                    forward difference).  s_offset [B] or [1] (offset_stride 1 / 0) is curr_state.position[0],
+ *                                    added to the states i >= 1 (:1190-1191).
+ * spectral_frenet_to_cartesian_device  frenet_to_cartesian3D() of src/cart_frenet.py:347-381: ref [n][6] = (rs, rx, ry, rtheta,
+ *                                    rkappa, rdkappa), s_cond [n][3], d_cond [n][3] -> out [n][6] = (x, y, v, a, theta, kappa). */
+int spectral_ego_states_device(spectral_handle_t *h, int B, const double *samples_dev, const int *npts_dev, int samples_cap,
+                               const double *s_offset_dev, int offset_stride, double *states_dev, void *cuda_stream);
+int spectral_frenet_to_cartesian_device(spectral_handle_t *h, long long n, const double *ref_dev, const double *s_cond_dev,
+                                        const double *d_cond_dev, double *out_dev, void *cuda_stream);
+
 /* Multi-GPU sweep: scenarios are sharded over ranks (one handle = one GPU = one rank); the ONLY exchange is
  * the best trajectory: local arg-min (k_argmin) -> NCCL all-gather of one 16-byte (cost, global index) record per rank ->
  * NCCL broadcast of the winner's (K, segments, control points) from the rank that owns it.  Ties -> lowest global index;

@@ -125,6 +125,9 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_get_work.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int]
     lib.spectral_get_class_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
     lib.spectral_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ubyte)]
+    lib.spectral_ego_states_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.spectral_frenet_to_cartesian_device.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 5
     lib.spectral_comm_unique_id.argtypes = [ctypes.POINTER(ctypes.c_ubyte)]
     lib.spectral_sweep_argmin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
@@ -398,6 +401,31 @@ class SpectralPlanner:
         segs = np.frombuffer(bytes(w.segs), dtype=CUBE_DTYPE)[:max(K, 0)].copy()
         return dict(cost=float(w.cost), index=int(w.index), rank=int(w.rank), K=K, segs=segs,
                     ctrl=np.array(w.ctrl[:12 * max(K, 0)], dtype=np.float64))
+
+    # ---- downstream of the path (run_ego / frenet_to_cartesian3D of src/cart_frenet.py), CUDA tensors in and out
+    def ego_states_device(self, samples, npts, s_offset, stream: Optional[int] = None):
+        """samples: float64 [B, cap, 6] (the `samples` output), npts: int32 [B], s_offset: float64 [B] or [1] -> float64 [B, cap, 4]."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        B, cap = int(samples.shape[0]), int(samples.shape[1])
+        states = torch.zeros(B, cap, 4, dtype=torch.float64, device=samples.device)
+        self._check(self._lib.spectral_ego_states_device(self._h, B, ctypes.c_void_p(samples.data_ptr()), ctypes.c_void_p(npts.data_ptr()), cap,
+                                                         ctypes.c_void_p(s_offset.data_ptr()), 1 if s_offset.numel() > 1 else 0,
+                                                         ctypes.c_void_p(states.data_ptr()), ctypes.c_void_p(stream)))
+        return states
+
+    def frenet_to_cartesian_device(self, ref, s_cond, d_cond, stream: Optional[int] = None):
+        """ref: float64 [n, 6], s_cond / d_cond: float64 [n, 3] -> float64 [n, 6] = (x, y, v, a, theta, kappa)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        n = int(ref.shape[0])
+        out = torch.empty(n, 6, dtype=torch.float64, device=ref.device)
+        self._check(self._lib.spectral_frenet_to_cartesian_device(self._h, n, ctypes.c_void_p(ref.data_ptr()), ctypes.c_void_p(s_cond.data_ptr()),
+                                                                  ctypes.c_void_p(d_cond.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                                  ctypes.c_void_p(stream)))
+        return out
 
     def launch_count(self) -> int:
         return int(self._lib.spectral_launch_count(self._h))

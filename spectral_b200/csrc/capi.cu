@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "corridor.cuh"
+#include "downstream.cuh"
 #include "finalize.cuh"
 #include "qp.cuh"
 #include "qp_dense.cuh"
@@ -114,6 +115,17 @@ __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a
                        else asm volatile("bar.sync 2, %0;" ::"n"(QpdLayout<KC>::TA) : "memory");
                      });
   }
+}
+
+// the step after the hot path (downstream.cuh)
+__global__ void k_ego_states(const double *samples, const int *npts, int cap, const double *s_offset, int off_stride, double *states, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (b < B && i < cap) ego_state_body(samples, npts, cap, s_offset, off_stride, states, b, i);
+}
+__global__ void k_frenet_to_cartesian(const double *ref, const double *s_cond, const double *d_cond, double *out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) frenet_to_cartesian_body(ref, s_cond, d_cond, out, (size_t)i);
 }
 
 // weight sweep: the corridor stage ran for scenario 0 only; every lane gets its (K, segments, corridor status)
@@ -788,6 +800,28 @@ extern "C" int spectral_argmin_device(spectral_handle_t *h, int B, const double 
   const int cap = h->sm_count * 4 < 1024 ? h->sm_count * 4 : 1024;
   if (blocks > cap) blocks = cap;
   k_argmin<<<blocks, 256, 0, st>>>(a_cost_dev, B, index_offset, h->partial, h->ticket, out_cost_dev, out_index_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
+// ------------------------------------------------------------------ downstream of the path
+extern "C" int spectral_ego_states_device(spectral_handle_t *h, int B, const double *samples_dev, const int *npts_dev, int samples_cap,
+                                          const double *s_offset_dev, int offset_stride, double *states_dev, void *cuda_stream) {
+  if (!h || B <= 0 || samples_cap <= 0 || !samples_dev || !npts_dev || !s_offset_dev || !states_dev) return SPECTRAL_ERR_INVALID;
+  if (B > 65535) return fail(h, SPECTRAL_ERR_CAPACITY, "ego states: at most 65535 scenarios per call");
+  CK(cudaSetDevice(h->device));
+  dim3 grid((samples_cap + 127) / 128, B);
+  k_ego_states<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(samples_dev, npts_dev, samples_cap, s_offset_dev, offset_stride ? 1 : 0, states_dev, B);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+extern "C" int spectral_frenet_to_cartesian_device(spectral_handle_t *h, long long n, const double *ref_dev, const double *s_cond_dev,
+                                                   const double *d_cond_dev, double *out_dev, void *cuda_stream) {
+  if (!h || n <= 0 || !ref_dev || !s_cond_dev || !d_cond_dev || !out_dev) return SPECTRAL_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  k_frenet_to_cartesian<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(ref_dev, s_cond_dev, d_cond_dev, out_dev, n);
   h->launches++;
   CK(cudaGetLastError());
   return SPECTRAL_SUCCESS;

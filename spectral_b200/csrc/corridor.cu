@@ -3,6 +3,8 @@
 // the segments must be bit-exact (see corridor.cuh).
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "corridor.cuh"
 
 __global__ void k_corridor(const CorridorArgs a) {
@@ -11,14 +13,22 @@ __global__ void k_corridor(const CorridorArgs a) {
   corridor_cta_body(a, b, threadIdx.x >> 5, threadIdx.x & 31, corridor_smem, []() { __syncthreads(); });
 }
 
-// cudaFuncSetAttribute applies to the CURRENT device: the caller (one handle per GPU) has set its device and remembers
-// the size it configured in *configured (per handle, so several handles / devices / threads in one process are fine).
+// cudaFuncSetAttribute applies to the CURRENT device and to the FUNCTION, not to a handle: two handles on one device
+// share the opt-in, so a handle that needs less must never lower what another one raised (that made the next R = 8
+// launch of the other handle fail with "invalid argument").  The size configured per device is kept here, under a
+// mutex (handles may live on different host threads); *configured mirrors it for the handle's diagnostics.
+static std::mutex g_corridor_mu;
+static int g_corridor_configured[64] = {};
 extern "C" int spectral_corridor_prepare(int N, int R, int *configured) {
   const CorridorSmem L = corridor_smem_layout(N, R);
-  if (L.total > *configured) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  std::lock_guard<std::mutex> lock(g_corridor_mu);
+  if (L.total > g_corridor_configured[dev]) {
     if (cudaFuncSetAttribute(k_corridor, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess) return -1;
-    *configured = L.total;
+    g_corridor_configured[dev] = L.total;
   }
+  *configured = g_corridor_configured[dev];
   return 0;
 }
 

@@ -399,6 +399,43 @@ def test_sweep_argmin_through_the_c_abi():
     pl.close()
 
 
+def test_downstream_ego_states_and_frenet_to_cartesian(planner):
+    """SURVEY.md 8f row 3 on the device: k_ego_states vs the reference's own run_ego() output (tests/golden/downstream.npz;
+    positions and the 0.01-rad headings bit-exact, speed to 1e-12: the reference takes `** 0.5`, the kernel sqrt), on a solved
+    batch vs the oracle restatement, and k_frenet_to_cartesian vs the reference's frenet_to_cartesian3D (1e-12 relative)."""
+    import torch
+    import downstream_oracle as dso
+    from test_oracle_golden import _rows_to_samples
+    dev = torch.device("cuda", 0)
+    z = H.golden("downstream")
+    for k in [k for k in z.files if k.endswith("/states")]:
+        rows = z[k.replace("/states", "/rows")]
+        off = float(k.split("/off")[1].split("/")[0])
+        smp = torch.from_numpy(_rows_to_samples(rows)[None].copy()).to(dev)
+        st = planner.ego_states_device(smp, torch.tensor([len(rows)], dtype=torch.int32, device=dev),
+                                       torch.tensor([off], dtype=torch.float64, device=dev)).cpu().numpy()[0]
+        assert np.array_equal(st[:, [0, 1, 3]], z[k][:, [0, 1, 3]]), k
+        assert np.allclose(st[:, 2], z[k][:, 2], rtol=1e-12, atol=0.0)
+    # a solved batch: every trajectory the product samples
+    batch = config2(256)
+    got = planner.solve("cub", batch, GOLDEN_W_CUB, samples_cap=96)
+    off = np.linspace(0.0, 25.5, 256)
+    st = planner.ego_states_device(torch.from_numpy(got.samples).to(dev), torch.from_numpy(got.npts).to(dev),
+                                   torch.from_numpy(off).to(dev)).cpu().numpy()
+    n_ok = 0
+    for b in np.nonzero(got.ok())[0]:
+        n = int(got.npts[b])
+        want = dso.ego_states(got.samples[b, :n], off[b])
+        assert np.array_equal(st[b, :n, [0, 1, 3]], want[:, [0, 1, 3]].T), b
+        assert np.allclose(st[b, :n, 2], want[:, 2], rtol=1e-12, atol=0.0)
+        assert not st[b, n:].any()
+        n_ok += 1
+    assert n_ok > 50
+    out = planner.frenet_to_cartesian_device(torch.from_numpy(z["f2c/ref"]).to(dev), torch.from_numpy(z["f2c/s_cond"]).to(dev),
+                                             torch.from_numpy(z["f2c/d_cond"]).to(dev)).cpu().numpy()
+    assert np.allclose(out, z["f2c/out"], rtol=1e-12, atol=1e-13), np.abs(out - z["f2c/out"]).max()
+
+
 def test_infeasibility_precheck_is_sound(planner):
     """Option infeasibility_precheck: every scenario it fails early is one the CONVERGED oracle fails too (and never one
     whose solved class the reference pins); every other scenario is bit-identical to the run without the option."""

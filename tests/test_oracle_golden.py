@@ -166,3 +166,51 @@ def test_config2_generator_contract():
     assert a.s_bounds.min() >= 0.0 and a.s_bounds.max() <= 50.0
     assert np.allclose(a.s_bounds, np.round(a.s_bounds, 2)) and np.allclose(a.l_bounds, np.round(a.l_bounds, 2))
     assert set(FEASIBLE) <= set(H.ALL_FIXTURES)
+
+
+# ---------------------------------------------------------------- downstream of the path
+def _rows_to_samples(rows):
+    """trajectory file rows `t s l ds dl dds ddl` -> the C-ABI sample layout (s, ds, dds, l, dl, ddl)."""
+    return np.stack([rows[:, 1], rows[:, 3], rows[:, 5], rows[:, 2], rows[:, 4], rows[:, 6]], axis=1)
+
+
+def test_downstream_oracle_equals_reference_functions():
+    """oracle/downstream_oracle.py vs tests/golden/downstream.npz, which the reference's OWN run_ego() and
+    frenet_to_cartesian3D() produced (oracle/gen_downstream_golden.py executes them from /root/reference): exact."""
+    import downstream_oracle as dso
+    z = H.golden("downstream")
+    keys = [k for k in z.files if k.endswith("/states")]
+    assert len(keys) == 4
+    for k in keys:
+        rows = z[k.replace("/states", "/rows")]
+        off = float(k.split("/off")[1].split("/")[0])
+        got = dso.ego_states(_rows_to_samples(rows), off)
+        assert np.array_equal(got, z[k]), k
+    out = np.array([dso.frenet_to_cartesian3d(z["f2c/ref"][i], z["f2c/s_cond"][i], z["f2c/d_cond"][i]) for i in range(len(z["f2c/ref"]))])
+    assert np.array_equal(out, z["f2c/out"])
+
+
+# ---------------------------------------------------------------- upstream of the path (SURVEY.md 8f row 1)
+def bounds_cases():
+    """(obstacles [(centre, vel_s, vel_l, horizon)], s_bounds [R][N][2], l_bounds [R][N][2]) of tests/golden/bounds.npz."""
+    z = H.golden("bounds")
+    for c in range(int(z["n_cases"])):
+        obs = [((r[0], r[1], r[2]), r[3], r[4], r[5]) for r in z["case%02d/obstacles" % c]]
+        yield c, obs, z["case%02d/s_bounds" % c], z["case%02d/l_bounds" % c]
+
+
+def test_bounds_oracle_equals_reference_get_bounds():
+    """oracle/bounds_oracle.py vs tests/golden/bounds.npz, which the reference's OWN Car / get_bounds / lineFromPoints
+    produced (oracle/gen_bounds_golden.py executes them from /root/reference/src/cart_frenet.py:644-1026): bit-exact
+    on all cases (1-3 obstacles, lateral overlaps, cars entering at t0 > 0)."""
+    import bounds_oracle as bo
+    n = 0
+    for c, obs, s_ref, l_ref in bounds_cases():
+        got = bo.get_bounds(obs)
+        s = np.array([g[0] for g in got])
+        l = np.array([g[1] for g in got])
+        assert s.shape == s_ref.shape, c
+        assert np.array_equal(s, s_ref), c
+        assert np.array_equal(np.broadcast_to(l[:, None, :], l_ref.shape), l_ref), c
+        n += 1
+    assert n >= 50

@@ -582,4 +582,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:  # a rank that dies must not leave its peers waiting in a collective until the launcher's timeout
+        if isinstance(exc, SystemExit) and exc.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

@@ -195,6 +195,21 @@ int spectral_solve_weights_device(spectral_handle_t *h, int variant, int B, int 
 int spectral_argmin_device(spectral_handle_t *h, int B, const double *a_cost_dev, long long index_offset,
                            double *out_cost_dev, long long *out_index_dev, void *cuda_stream);
 
+/* Upstream of the path, device buffers, enqueued on cuda_stream: the reference's bound generator
+ * src/cart_frenet.py:644-807 (Car.getCar: obstacle -> space-time prism, lateral edges), :819-830 (lineFromPoints, 0.01 rounding),
+ * :833-1026 (get_bounds, 'yield' homotopy), called as in :1539-1557.
+ *   obstacles [B][M][6] = (s, l, t0, vel_s, vel_l, horizon) in creation order, M <= 4; n_obs [B] (NULL: M everywhere);
+ *   road[4] = (s_l_l, s_u_l, d_l_l, d_u_l) (cart_frenet.py:54-58: 0, 50, -2, 8)
+ *   -> s_bounds, l_bounds [B][R_cap][N][2] in the layout of SpectralInputs and n_lanes [B] = lanes of the road found.
+ * Lanes r >= n_lanes[b] are written as EMPTY lanes (l_lo = 1 > l_hi = -1, s = the free road): CollisionCheck's lateral test
+ * (solve_3d.cc:534) never selects a cube of such a region, so spectral_solve_batch_device(.., R = R_cap, ..) on these arrays
+ * gives the corridors and trajectories of the unpadded scenarios.  n_lanes[b] = -1: more lanes than R_cap (or than the
+ * kernel's tables hold); all R_cap lanes of that scenario are then written empty, so a solve on them reports SPECTRAL_FAIL_NO_CORRIDOR.  Bit-identical to the reference's get_bounds on its
+ * specified domain (cars whose smallest lateral edges tie are ordered by object hash there: creation order here). */
+int spectral_bounds_device(spectral_handle_t *h, int B, int N, int M, const double *obstacles_dev, const int *n_obs_dev,
+                           const double road[4], int R_cap, double *s_bounds_dev, double *l_bounds_dev, int *n_lanes_dev,
+                           void *cuda_stream);
+
 /* Downstream of the path, device buffers, enqueued on cuda_stream:
  * spectral_ego_states_device         run_ego() of src/cart_frenet.py:1126-1221: samples [B][cap][6] (the `samples` output:
  *                                    s, ds, dds, l, dl, ddl) + npts [B] -> states [B][cap][4] = (position along the road,

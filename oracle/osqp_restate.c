@@ -630,6 +630,12 @@ int osqp_restate_solve(ll n, ll m, const ll *Pp, const ll *Pi, const double *Px_
   if (s->adaptive_rho && adapt_interval == 0)
     adapt_interval = s->check_termination ? 4 * s->check_termination : 100;
   if (ldl_numeric(&w->F, w->K.p, w->K.i, w->K.x) != 0) { status = OSQP_RESTATE_NON_CVX; goto done; }
+  /* OSQP's validate_data (called by osqp_setup): "Lower bound at index i is greater than upper bound" -> setup fails and
+   * no iteration runs.  (The reference then dereferences the NULL workspace, solve_3d.cc:1251 -- undefined; the restatement
+   * reports the problem as unsolved after 0 iterations, which the wrapper maps to its failure sentinel.)  Checked on the
+   * caller's unscaled bounds like OSQP does. */
+  for (ll i = 0; i < m; i++)
+    if (l[i] > u[i]) { status = OSQP_RESTATE_UNSOLVED; iter = 0; goto done; }
 
   for (iter = 1; iter <= s->max_iter; iter++) {
     double *t;

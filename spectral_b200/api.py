@@ -87,6 +87,9 @@ class Params(ctypes.Structure):
 _lib = None
 
 
+ROAD = (0.0, 50.0, -2.0, 8.0)   # s_l_l, s_u_l, d_l_l, d_u_l of the reference's road (src/cart_frenet.py:54-58)
+
+
 def lib_path(name: str = "libspectral.so") -> str:
     return os.path.join(LIB_DIR, name)
 
@@ -125,6 +128,8 @@ def load_library() -> ctypes.CDLL:
     lib.spectral_get_work.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int]
     lib.spectral_get_class_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
     lib.spectral_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ubyte)]
+    lib.spectral_bounds_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _dp,
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.spectral_ego_states_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     lib.spectral_frenet_to_cartesian_device.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 5
@@ -401,6 +406,25 @@ class SpectralPlanner:
         segs = np.frombuffer(bytes(w.segs), dtype=CUBE_DTYPE)[:max(K, 0)].copy()
         return dict(cost=float(w.cost), index=int(w.index), rank=int(w.rank), K=K, segs=segs,
                     ctrl=np.array(w.ctrl[:12 * max(K, 0)], dtype=np.float64))
+
+    # ---- upstream of the path (Car.getCar / get_bounds of src/cart_frenet.py:644-1026), CUDA tensors in and out
+    def bounds_device(self, obstacles, n_knots: int, r_cap: int, n_obs=None, road=ROAD, stream: Optional[int] = None):
+        """obstacles: float64 [B, M, 6] = (s, l, t0, vel_s, vel_l, horizon) per obstacle, creation order; n_obs: int32 [B] or None.
+        Returns (s_bounds [B, r_cap, N, 2], l_bounds [B, r_cap, N, 2], n_lanes int32 [B]); lanes >= n_lanes[b] are empty lanes
+        (never selected by the corridor stage), so the pair feeds solve_device with n_regions = r_cap."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        B, M = int(obstacles.shape[0]), int(obstacles.shape[1])
+        sb = torch.empty(B, r_cap, n_knots, 2, dtype=torch.float64, device=obstacles.device)
+        lb = torch.empty(B, r_cap, n_knots, 2, dtype=torch.float64, device=obstacles.device)
+        nl = torch.empty(B, dtype=torch.int32, device=obstacles.device)
+        rd = (ctypes.c_double * 4)(*[float(v) for v in road])
+        self._check(self._lib.spectral_bounds_device(self._h, B, n_knots, M, ctypes.c_void_p(obstacles.data_ptr()),
+                                                     ctypes.c_void_p(n_obs.data_ptr()) if n_obs is not None else None, rd, r_cap,
+                                                     ctypes.c_void_p(sb.data_ptr()), ctypes.c_void_p(lb.data_ptr()),
+                                                     ctypes.c_void_p(nl.data_ptr()), ctypes.c_void_p(stream)))
+        return sb, lb, nl
 
     # ---- downstream of the path (run_ego / frenet_to_cartesian3D of src/cart_frenet.py), CUDA tensors in and out
     def ego_states_device(self, samples, npts, s_offset, stream: Optional[int] = None):

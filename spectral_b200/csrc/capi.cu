@@ -14,6 +14,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "bounds.cuh"
 #include "corridor.cuh"
 #include "downstream.cuh"
 #include "finalize.cuh"
@@ -27,6 +28,7 @@ static_assert(SPECTRAL_NUM_CLASSES == SP_NUM_CLASSES && SPECTRAL_NUM_WORK >= 6 +
 
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
 extern "C" int spectral_corridor_prepare(int N, int R, int *configured);                           // corridor.cu
+extern "C" void spectral_launch_bounds(const BoundsArgs &a, cudaStream_t st);                      // corridor.cu (same --fmad=false unit)
 
 // ------------------------------------------------------------------ kernels
 __global__ void k_tables(const double *weights, double *mqm, int W) {
@@ -800,6 +802,21 @@ extern "C" int spectral_argmin_device(spectral_handle_t *h, int B, const double 
   const int cap = h->sm_count * 4 < 1024 ? h->sm_count * 4 : 1024;
   if (blocks > cap) blocks = cap;
   k_argmin<<<blocks, 256, 0, st>>>(a_cost_dev, B, index_offset, h->partial, h->ticket, out_cost_dev, out_index_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
+// ------------------------------------------------------------------ upstream of the path
+extern "C" int spectral_bounds_device(spectral_handle_t *h, int B, int N, int M, const double *obstacles_dev, const int *n_obs_dev,
+                                      const double road[4], int R_cap, double *s_bounds_dev, double *l_bounds_dev, int *n_lanes_dev,
+                                      void *cuda_stream) {
+  if (!h || !obstacles_dev || !road || !s_bounds_dev || !l_bounds_dev || !n_lanes_dev) return SPECTRAL_ERR_INVALID;
+  if (B <= 0 || N < 3 || N > h->n_max || M < 1 || M > SPB_MAX_CARS || R_cap < 1 || R_cap > SPB_MAX_LANES)
+    return fail(h, SPECTRAL_ERR_CAPACITY, "bounds: shape exceeds the capacity (obstacles per scenario <= 4, lanes <= 24)");
+  CK(cudaSetDevice(h->device));
+  BoundsArgs a{B, N, M, R_cap, obstacles_dev, n_obs_dev, road[0], road[1], road[2], road[3], s_bounds_dev, l_bounds_dev, n_lanes_dev};
+  spectral_launch_bounds(a, (cudaStream_t)cuda_stream);
   h->launches++;
   CK(cudaGetLastError());
   return SPECTRAL_SUCCESS;

@@ -41,6 +41,7 @@ SP_DEV double rn_add(double a, double b) { return __dadd_rn(a, b); }
 SP_DEV double rn_sub(double a, double b) { return __dsub_rn(a, b); }
 SP_DEV double rn_mul(double a, double b) { return __dmul_rn(a, b); }
 SP_DEV double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+SP_DEV void sp_store2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }  // p 16-byte aligned
 #endif
 
 // group (sub-warp) reductions over `width` consecutive lanes, width a power of two

@@ -5,6 +5,7 @@
 
 #include <mutex>
 
+#include "bounds.cuh"
 #include "corridor.cuh"
 
 __global__ void k_corridor(const CorridorArgs a) {
@@ -36,3 +37,10 @@ extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st)
   const CorridorSmem L = corridor_smem_layout(a.N, a.R);
   k_corridor<<<a.B, 32 * a.R, L.total, st>>>(a);
 }
+
+// upstream bound generator (bounds.cuh): one warp per scenario, four scenarios per CTA
+__global__ void __launch_bounds__(128) k_bounds(const BoundsArgs a) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b < a.B) bounds_warp_body(a, b, threadIdx.x & 31);
+}
+extern "C" void spectral_launch_bounds(const BoundsArgs &a, cudaStream_t st) { k_bounds<<<(a.B + 3) / 4, 128, 0, st>>>(a); }

@@ -570,14 +570,16 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
   // k - 1 and row 0 of segment k bound the same quantity, t_{k-1} c_{k-1,5} = t_k c_{k,0}); the initial state lies inside
   // the first segment's position / velocity / acceleration rows (rows 18..20 are equalities on the expressions of rows
   // 0, 6, 11).  OR-ed over the JW lanes that form one OSQP instance.
+  // Always: OSQP's validate_data (run by osqp_setup) refuses a problem with a row l > u before the first iteration (the
+  // reference then dereferences the NULL workspace, solve_3d.cc:1251); such a scenario fails with 0 iterations here.
   int pre = 0;
+  bool bad = false;
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 18; r++) bad = bad || (lo[r] > hi[r]);
+  }
   if (o.precheck) {
     const double mg = o.precheck_margin;
-    bool bad = false;
-    if (active) {
-#pragma unroll
-      for (int r = 0; r < 18; r++) bad = bad || (lo[r] > hi[r] + mg);
-    }
     const double plo = sp_shfl_up(lo[5], 1, LPA), phi = sp_shfl_up(hi[5], 1, LPA);
     if (active && !first) {
       const double jl = lo[0] > plo ? lo[0] : plo, jh = hi[0] < phi ? hi[0] : phi;
@@ -588,8 +590,8 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
       bad = bad || (lo[19] > hi[6] + mg) || (lo[19] < lo[6] - mg);
       bad = bad || (lo[20] > hi[11] + mg) || (lo[20] < lo[11] - mg);
     }
-    pre = qp_joint_or<JW>(bad ? 1 : 0, xch);
   }
+  pre = qp_joint_or<JW>(bad ? 1 : 0, xch);
   if (a.lu != nullptr && active) {
     double *dst = a.lu + (((size_t)b * 2 + axis) * a.k_max + seg) * QP_ROWS * 2;
 #pragma unroll

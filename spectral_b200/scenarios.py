@@ -177,3 +177,31 @@ def zigzag_breaks(base: Scenario, B: int, seed: int = 4242, s_max: float = 100.0
     s[:, :, :, 1] = np.maximum(s[:, :, :, 1] - stair[:, None, :], s[:, :, :, 0])
     return ScenarioBatch(N, batch.n_regions, batch.delta_t, s, batch.l_bounds, batch.ds_bounds, batch.dl_bounds, batch.s_ref,
                          batch.l_ref, batch.init, batch.scalars)
+
+
+def random_obstacles(B: int, max_obs: int = 3, seed: int = 20230606):
+    """Obstacle sets for the upstream bound generator (spectral_bounds_device): [B, max_obs, 6] = (s, l, t0, vel_s, vel_l,
+    horizon) and n_obs [B], with the value ranges of the reference's two-car scene (src/cart_frenet.py:1536-1546): lateral
+    positions on a 0.25 m grid so that lane edges coincide now and then, 60 % of the cars present from t = 0 (they bound s from
+    above), the others entering later (they bound s from below).  Scenarios whose cars tie in their smallest lateral edge are
+    re-drawn: the reference orders such cars by object hash (not specified)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    obs = np.zeros((B, max_obs, 6))
+    n_obs = np.zeros(B, np.int32)
+    w_safe = 2 / 3 + 2 / 3
+    for b in range(B):
+        while True:
+            n = int(rng.integers(1, max_obs + 1))
+            o = np.zeros((max_obs, 6))
+            o[:n, 0] = np.round(rng.uniform(2.0, 35.0, n), 1)
+            o[:n, 1] = rng.integers(-4, 25, n) * 0.25
+            o[:n, 2] = np.where(rng.random(n) < 0.6, 0.0, np.round(rng.uniform(0.5, 3.0, n), 1))
+            o[:n, 3] = np.round(rng.uniform(1.0, 8.0, n), 1)
+            o[:n, 4] = rng.choice([0.0, 0.0, 0.25, -0.25, 0.5], n)
+            o[:n, 5] = rng.choice([3.0, 4.0, 5.0], n)
+            fl = o[:n, 1] + o[:n, 4] * o[:n, 5]
+            lo = np.where(o[:n, 4] >= 0, o[:n, 1] - w_safe, fl - w_safe)
+            if len(set(lo.tolist())) == n:
+                break
+        obs[b], n_obs[b] = o, n
+    return obs, n_obs

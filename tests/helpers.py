@@ -103,6 +103,44 @@ def emu_solve(variant, batch, weights, k_max=32, samples_cap=0, want_lu=False, *
     return res
 
 
+def emu_bounds(obstacles, n_obs, n_knots, r_cap, road=api.ROAD):
+    """bounds.cuh's warp body on the host (tests/warp_emu): (s_bounds, l_bounds, n_lanes)."""
+    emu = emu_lib()
+    obstacles = np.ascontiguousarray(obstacles, dtype=np.float64)
+    B, M = obstacles.shape[:2]
+    n_obs = np.ascontiguousarray(n_obs, dtype=np.int32)
+    sb = np.full((B, r_cap, n_knots, 2), np.nan)
+    lb = np.full((B, r_cap, n_knots, 2), np.nan)
+    nl = np.zeros(B, np.int32)
+    emu.emu_bounds(B, n_knots, M, r_cap, api._d(obstacles), api._i(n_obs), api._d(np.array(road, dtype=np.float64)), api._d(sb), api._d(lb),
+                   api._i(nl))
+    return sb, lb, nl
+
+
+def assert_bounds_equal_oracle(sb, lb, nl, obstacles, n_obs, n_knots, r_cap, road=api.ROAD):
+    """(s_bounds, l_bounds, n_lanes) of the bounds kernel vs oracle/bounds_oracle.py (pinned to the reference's get_bounds), bit for bit;
+    the padding lanes are empty lanes over the free road.  Lane-table overflows of the kernel's small fixed tables may only
+    happen where the oracle's lane count exceeds r_cap."""
+    import bounds_oracle as bo
+    rd = dict(s_l_l=road[0], s_u_l=road[1], d_l_l=road[2], d_u_l=road[3])
+    n_over = 0
+    for b in range(len(nl)):
+        obs = [((o[0], o[1], o[2]), o[3], o[4], o[5]) for o in obstacles[b, :n_obs[b]]]
+        want = bo.get_bounds(obs, n_knots, rd)
+        if len(want) > r_cap:
+            assert nl[b] == -1, b
+            assert np.all(lb[b, :, :, 0] == 1.0) and np.all(lb[b, :, :, 1] == -1.0), b
+            n_over += 1
+            continue
+        assert nl[b] == len(want), (b, nl[b], len(want))
+        for r, (s, (lo, hi)) in enumerate(want):
+            assert np.array_equal(sb[b, r], s), (b, r)
+            assert np.all(lb[b, r, :, 0] == lo) and np.all(lb[b, r, :, 1] == hi), (b, r)
+        assert np.all(sb[b, len(want):, :, 0] == road[0]) and np.all(sb[b, len(want):, :, 1] == road[1]), b
+        assert np.all(lb[b, len(want):, :, 0] == 1.0) and np.all(lb[b, len(want):, :, 1] == -1.0), b
+    return n_over
+
+
 def decided_classes(ref, ref0, max_iter=5000, early_frac=0.6):
     """Which scenarios have a solved/failed class that the reference itself pins.
 

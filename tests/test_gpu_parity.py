@@ -399,6 +399,49 @@ def test_sweep_argmin_through_the_c_abi():
     pl.close()
 
 
+def test_upstream_bounds_kernel_and_obstacle_driven_solve(planner):
+    """SURVEY.md 8f row 1 on the device: k_bounds vs the reference's own get_bounds output (tests/golden/bounds.npz) and vs the
+    pinned oracle on 6 000 random obstacle sets -- bit for bit; then the obstacle-driven pipeline k_bounds -> corridor -> QP with
+    no bounds upload: identical to the host-buffer solve of the same (padded) bounds, and in parity with the CPU oracle."""
+    import torch
+    from spectral_b200.scenarios import random_obstacles
+    from test_oracle_golden import bounds_cases
+    dev = torch.device("cuda", 0)
+    for c, obs, s_ref, l_ref in bounds_cases():
+        o = torch.tensor([[[cc[0], cc[1], cc[2], vs, vl, T] for cc, vs, vl, T in obs]], dtype=torch.float64, device=dev)
+        sb, lb, nl = planner.bounds_device(o, s_ref.shape[1], len(s_ref))
+        assert int(nl[0]) == len(s_ref), c
+        assert np.array_equal(sb[0].cpu().numpy(), s_ref) and np.array_equal(lb[0].cpu().numpy(), l_ref), c
+    obs, n_obs = random_obstacles(6000, max_obs=4, seed=11)
+    sb, lb, nl = planner.bounds_device(torch.from_numpy(obs).to(dev), 71, 12, n_obs=torch.from_numpy(n_obs).to(dev))
+    n_over = H.assert_bounds_equal_oracle(sb.cpu().numpy(), lb.cpu().numpy(), nl.cpu().numpy(), obs, n_obs, 71, 12)
+    assert n_over < 300
+    # obstacle-driven solve: 384 sets of one or two cars on the c1 scene (references, derivative bounds, initial state of c1)
+    B, R = 384, 8
+    obs, n_obs = random_obstacles(B, max_obs=2, seed=5)
+    base = load_fixture("c1")
+    d_obs = torch.from_numpy(obs).to(dev)
+    sb, lb, nl = planner.bounds_device(d_obs, base.n_knots, R, n_obs=torch.from_numpy(n_obs).to(dev))
+    assert int(nl.min()) >= 2
+    tile = lambda a: np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))  # noqa: E731
+    init = np.concatenate([base.init_s, base.init_l])
+    padded = ScenarioBatch(base.n_knots, R, base.delta_t, sb.cpu().numpy(), lb.cpu().numpy(), tile(base.ds_bounds), tile(base.dl_bounds),
+                           tile(base.s_ref), tile(base.l_ref), tile(init), tile(base.scalars))
+    inputs = dict(s_bounds=sb, l_bounds=lb, weights=torch.tensor(GOLDEN_W_TRP, dtype=torch.float64, device=dev))
+    for k in ("ds_bounds", "dl_bounds", "s_ref", "l_ref", "init", "scalars"):
+        inputs[k] = torch.from_numpy(getattr(padded, k)).to(dev)
+    outs = planner.alloc_device_outputs(B)
+    planner.solve_device("trp", base.n_knots, R, base.delta_t, inputs, outs)
+    torch.cuda.synchronize()
+    got = planner.solve("trp", padded, GOLDEN_W_TRP)
+    assert np.array_equal(outs["K"].cpu().numpy(), got.K) and np.array_equal(outs["status"].cpu().numpy(), got.status)
+    assert np.array_equal(outs["ctrl"].cpu().numpy(), got.ctrl) and np.array_equal(outs["a_cost"].cpu().numpy(), got.a_cost)
+    ref, ref0 = H.oracle_pair("trp", padded, GOLDEN_W_TRP)
+    got0 = planner.solve("trp", padded, GOLDEN_W_TRP, options=api.default_options(polish=0))
+    H.assert_batch_parity(got, ref, "obstacle-driven", ref0=ref0, batch=padded, variant="trp", weights=GOLDEN_W_TRP, got0=got0)
+    assert got.ok().sum() > B // 8
+
+
 def test_downstream_ego_states_and_frenet_to_cartesian(planner):
     """SURVEY.md 8f row 3 on the device: k_ego_states vs the reference's own run_ego() output (tests/golden/downstream.npz;
     positions and the 0.01-rad headings bit-exact, speed to 1e-12: the reference takes `** 0.5`, the kernel sqrt), on a solved

@@ -179,18 +179,21 @@ def test_config3_groups_share_one_kkt_structure():
 
 # ---------------------------------------------------------------- the reference's OWN wrapper modules, unchanged
 REF_SRC = "/root/reference/src"
+REF_PYC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "wrappers")   # oracle/Makefile
 REF_LIB_DIR = "/home/srujan_d/RISS/code/btrapz/src"   # the literal path the wrappers CDLL() (trp_wrapper.py:45, cub_wrapper.py)
 
 
 def _stage_reference_wrapper(tmp_path, monkeypatch, module):
     """Installs OUR libtrp.so / libcub.so / libspectral.so at the literal path the reference's wrapper loads from, puts a
     stub `optuna` on sys.path (the wrappers import it at module top, trp_wrapper.py:3; it is not installed here) and imports
-    the reference's module from /root/reference/src WITHOUT editing it."""
+    the reference's module from /root/reference/src WITHOUT editing it (on the GPU box, which has no /root/reference: from the
+    byte-compiled modules oracle/Makefile made of those files, oracle/_ref/wrappers/*.pyc -- same code objects, no source)."""
     import importlib
     import shutil
     import sys
-    if not os.path.isdir(REF_SRC):
-        pytest.skip("/root/reference is not present on this machine (the wrapper sources may not be copied into the repo)")
+    src = REF_SRC if os.path.isdir(REF_SRC) else REF_PYC   # the sources where they lie, else their byte-compiled form
+    if not os.path.exists(os.path.join(src, module + (".py" if src == REF_SRC else ".pyc"))):
+        pytest.skip("neither /root/reference nor oracle/_ref/wrappers (built by oracle/Makefile) is present on this machine")
     try:
         os.makedirs(REF_LIB_DIR, exist_ok=True)
     except OSError:
@@ -201,7 +204,7 @@ def _stage_reference_wrapper(tmp_path, monkeypatch, module):
     stub.mkdir()
     (stub / "optuna.py").write_text("def create_study(*a, **k):\n    raise RuntimeError('stub')\n")
     monkeypatch.syspath_prepend(str(stub))
-    monkeypatch.syspath_prepend(REF_SRC)
+    monkeypatch.syspath_prepend(src)
     sys.modules.pop(module, None)
     return importlib.import_module(module)
 

@@ -134,3 +134,45 @@ def test_emu_infeasibility_precheck():
     assert list(on.iters) == [100, 0, 100, 0]
     assert on.status[1] == on.status[3] == api.FAIL_SOLVER and on.a_cost[1] == api.FAIL_COST
     assert np.array_equal(on.ctrl[[0, 2]], off.ctrl[[0, 2]])
+
+
+# ---------------------------------------------------------------- upstream bound generator (bounds.cuh)
+def test_emu_bounds_kernel_equals_reference_goldens():
+    """bounds.cuh's warp body vs tests/golden/bounds.npz (the reference's OWN Car / get_bounds, executed from its source): the
+    region bounds bit for bit on all 58 obstacle sets."""
+    from test_oracle_golden import bounds_cases
+    n = 0
+    for c, obs, s_ref, l_ref in bounds_cases():
+        o = np.array([[cc[0], cc[1], cc[2], vs, vl, T] for cc, vs, vl, T in obs])[None]
+        R = len(s_ref)
+        sb, lb, nl = H.emu_bounds(o, [len(obs)], s_ref.shape[1], R)
+        assert nl[0] == R, (c, nl[0], R)
+        assert np.array_equal(sb[0], s_ref), c
+        assert np.array_equal(lb[0], l_ref), c
+        n += 1
+    assert n >= 50
+
+
+def test_emu_bounds_kernel_random_obstacles_and_padding():
+    """2 000 random obstacle sets (1-4 cars) vs the pinned oracle, with the output padded to 12 lanes; and the padding lanes
+    are inert: the corridor stage on the padded regions gives the corridors of the unpadded scenario."""
+    from spectral_b200.scenarios import random_obstacles
+    obs, n_obs = random_obstacles(2000, max_obs=4, seed=7)
+    sb, lb, nl = H.emu_bounds(obs, n_obs, 71, 12)
+    n_over = H.assert_bounds_equal_oracle(sb, lb, nl, obs, n_obs, 71, 12)
+    assert n_over < 100 and (nl > 0).sum() > 1900
+    assert len(np.unique(nl)) >= 6
+    # padding is inert for the corridor stage: fixture c1 (2 regions) padded with 3 empty lanes
+    base = H.fixture_batch("c1")
+    N = base.n_knots
+    pad_s = np.tile(np.array([0.0, 50.0]), (1, 3, N, 1))
+    pad_l = np.tile(np.array([1.0, -1.0]), (1, 3, N, 1))
+    padded = ScenarioBatch(N, base.n_regions + 3, base.delta_t, np.concatenate([base.s_bounds, pad_s], 1), np.concatenate([base.l_bounds, pad_l], 1),
+                           base.ds_bounds, base.dl_bounds, base.s_ref, base.l_ref, base.init, base.scalars)
+    for variant in H.VARIANTS:
+        a = po.solve_batch(variant, base, WEIGHTS_FILE, mode=0, nthreads=1)
+        b = po.solve_batch(variant, padded, WEIGHTS_FILE, mode=0, nthreads=1)
+        assert a["K"][0] == b["K"][0] and H.segs_equal(a["segs"][0], b["segs"][0], int(a["K"][0]))
+        assert np.array_equal(a["ctrl"], b["ctrl"])
+        g = H.emu_solve(variant, padded, WEIGHTS_FILE, max_iter=25, polish=0)
+        assert g.K[0] == a["K"][0] and H.segs_equal(g.segs[0], a["segs"][0], int(a["K"][0]))

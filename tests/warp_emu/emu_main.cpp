@@ -5,6 +5,7 @@
 // exists.  Not part of the product.
 #define SPECTRAL_CPU_EMU 1
 #include "../../spectral_b200/csrc/common.cuh"
+#include "../../spectral_b200/csrc/bounds.cuh"
 #include "../../spectral_b200/csrc/corridor.cuh"
 #include "../../spectral_b200/csrc/qp.cuh"
 #include "../../spectral_b200/csrc/qp_dense.cuh"
@@ -153,4 +154,12 @@ extern "C" void emu_default_options(SpectralOptions *o) {
   o->alpha = 1.6; o->scaling = 4; o->check_termination = 25; o->adaptive_rho_interval = 100;
   o->adaptive_rho_tolerance = 5.0; o->polish = 1; o->polish_delta = 1e-6; o->polish_refine_iter = 4; o->polish_rounds = 8;
   o->infeasibility_precheck = 0; o->precheck_margin = 1e-3; o->shared_kkt = 0;
+}
+
+// upstream bound generator (bounds.cuh): the warp body has no warp collectives, so the 32 lanes run one after the other
+extern "C" void emu_bounds(int B, int N, int M, int R_cap, const double *obstacles, const int *n_obs, const double *road, double *s_bounds,
+                           double *l_bounds, int *n_lanes) {
+  BoundsArgs a{B, N, M, R_cap, obstacles, n_obs, road[0], road[1], road[2], road[3], s_bounds, l_bounds, n_lanes};
+  for (int b = 0; b < B; b++)
+    for (int lane = 0; lane < 32; lane++) bounds_warp_body(a, b, lane);
 }

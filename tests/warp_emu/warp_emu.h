@@ -78,3 +78,4 @@ inline double rn_add(double a, double b) { return a + b; }
 inline double rn_sub(double a, double b) { return a - b; }
 inline double rn_mul(double a, double b) { return a * b; }
 inline double rn_div(double a, double b) { return a / b; }
+inline void sp_store2(double *p, double a, double b) { p[0] = a; p[1] = b; }

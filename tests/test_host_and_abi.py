@@ -191,22 +191,31 @@ def _stage_reference_wrapper(tmp_path, monkeypatch, module):
     import importlib
     import shutil
     import sys
-    src = REF_SRC if os.path.isdir(REF_SRC) else REF_PYC   # the sources where they lie, else their byte-compiled form
-    if not os.path.exists(os.path.join(src, module + (".py" if src == REF_SRC else ".pyc"))):
+    pyc = os.path.join(REF_PYC, module + ".pyc.bin")
+    if not os.path.isdir(REF_SRC) and not os.path.exists(pyc):
         pytest.skip("neither /root/reference nor oracle/_ref/wrappers (built by oracle/Makefile) is present on this machine")
     try:
         os.makedirs(REF_LIB_DIR, exist_ok=True)
     except OSError:
         pytest.skip("cannot create " + REF_LIB_DIR)
     for name in ("libspectral.so", "libtrp.so", "libcub.so"):
-        shutil.copy(api.lib_path(name), os.path.join(REF_LIB_DIR, name))
+        # (copy + rename: an earlier test of this process may still have the old file mapped; writing into it in place crashes)
+        shutil.copy(api.lib_path(name), os.path.join(REF_LIB_DIR, name + ".new"))
+        os.replace(os.path.join(REF_LIB_DIR, name + ".new"), os.path.join(REF_LIB_DIR, name))
     stub = tmp_path / "stub"
     stub.mkdir()
     (stub / "optuna.py").write_text("def create_study(*a, **k):\n    raise RuntimeError('stub')\n")
     monkeypatch.syspath_prepend(str(stub))
-    monkeypatch.syspath_prepend(src)
     sys.modules.pop(module, None)
-    return importlib.import_module(module)
+    if os.path.isdir(REF_SRC):     # the sources where they lie
+        monkeypatch.syspath_prepend(REF_SRC)
+        return importlib.import_module(module)
+    import importlib.machinery     # their byte-compiled form (same code objects)
+    import importlib.util
+    loader = importlib.machinery.SourcelessFileLoader(module, pyc)
+    mod = importlib.util.module_from_spec(importlib.util.spec_from_loader(module, loader))
+    loader.exec_module(mod)
+    return mod
 
 
 @pytest.mark.parametrize("module", ["trp_wrapper", "cub_wrapper"])

@@ -85,18 +85,34 @@ __global__ void __launch_bounds__(32 * WPB) k_qp(const QpArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // LPA = 32 (K > 16): the block's two warps are the s-axis and the l-axis problem of ONE scenario, solved jointly (JW = 64)
   static_assert(LPA < 32 || WPB == 2, "a two-warp CTA per scenario");
-  qp_warp_body<LPA, 2 * LPA>(a, blockIdx.x * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32,
-                             qp_smem + (size_t)WPB * QP_SM_DOUBLES_PER_LANE * 32);
+  // grid-stride over the class' scenarios: the launch holds at most a few CTAs per SM, not one per scenario of the batch
+  constexpr int G = 32 / LPA;
+  const int nblk = (2 * *a.count + G * WPB - 1) / (G * WPB);
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    qp_warp_body<LPA, 2 * LPA>(a, blk * WPB + warp, lane, qp_smem + (size_t)warp * QP_SM_DOUBLES_PER_LANE * 32,
+                               qp_smem + (size_t)WPB * QP_SM_DOUBLES_PER_LANE * 32);
+    __syncthreads();
+  }
 }
 
 // dense-operator ADMM kernel (qp_dense.cuh): one CTA (2 TA threads) per scenario of this class
 #ifndef QPD_MINBLOCKS
 #define QPD_MINBLOCKS(KC) ((KC) <= 10 ? 2 : 1)  // CTAs per SM the register budget is capped for
 #endif
+// Persistent like k_qpa: QPD_MINBLOCKS CTAs per SM take scenarios of the class from the device-side queue (a.next) until
+// the list is drained, so a launch never holds more CTAs than the class has work for (was: B CTAs, most of them empty).
 template <int KC>
 __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, QPD_MINBLOCKS(KC)) k_qpd(const QpArgs a) {
   extern __shared__ __align__(16) double qpd_smem[];
-  qpd_cta_body<KC>(a, blockIdx.x, threadIdx.x, qpd_smem, []() { __syncthreads(); });
+  __shared__ int s_slot;
+  for (;;) {
+    if (threadIdx.x == 0) s_slot = atomicAdd(a.next, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    __syncthreads();
+    if (slot >= *a.count) return;
+    qpd_cta_body<KC>(a, slot, threadIdx.x, qpd_smem, []() { __syncthreads(); });
+  }
 }
 
 // anchor-layout dense ADMM kernel (qp_anchor.cuh), KC <= 10.  Persistent: 2 CTAs per SM take scenarios of this class from
@@ -487,7 +503,8 @@ static cudaError_t launch_qpd(spectral_handle *h, const QpArgs &qa, int B, cudaS
   const size_t smem = QpdLayout<KC>::BYTES;
   cudaError_t e = cudaFuncSetAttribute(k_qpd<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_qpd<KC><<<B, 2 * QpdLayout<KC>::TA, smem, st>>>(qa);
+  const int cap = QPD_MINBLOCKS(KC) * h->sm_count;
+  k_qpd<KC><<<B < cap ? B : cap, 2 * QpdLayout<KC>::TA, smem, st>>>(qa);
   h->launches++;
   return cudaGetLastError();
 }
@@ -565,7 +582,8 @@ static cudaError_t launch_qp(spectral_handle *h, const QpArgs &qa, int B, cudaSt
   if (e != cudaSuccess) return e;
   const int warps = (2 * B + G - 1) / G;
   const int blocks = (warps + WPB - 1) / WPB;
-  k_qp<LPA, WPB><<<blocks, 32 * WPB, smem, st>>>(qa);
+  const int cap = 8 * h->sm_count;
+  k_qp<LPA, WPB><<<blocks < cap ? blocks : cap, 32 * WPB, smem, st>>>(qa);
   h->launches++;
   return cudaGetLastError();
 }

@@ -44,6 +44,7 @@ struct QpaIO {
   int live;   // bits 0..4: slot holds a live row (rho > 0 possible), bit 5: the join slot is the primary copy
   int kj;     // segment of the join row
   int state, need_g, it;
+  int K;      // segment count of the scenario (the check would otherwise chase a.K[a.list[slot]] through L2 every 25 iterations)
 };
 
 // thread map: ta in [0, TA) -> (variable v or -1)
@@ -186,7 +187,6 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
   const int axis = tid / TA, ta = tid - axis * TA;
   double *smx = smem + axis * L::AXIS;
   double *red = smem + L::O_RED;
-  const int K = a.K[a.list[slot]];
   const double *ctl = smx + L::O_CTRL;
   const double *lsx = smx + L::O_LS;
   int seg, i;
@@ -195,16 +195,26 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
   const int v = isvar ? 6 * seg + i : 0;
   const int jsrc = 6 * (lane / 6) + 3 * (i / 3);
   double *xr = smx + L::O_XR;
-  const double c_scale = io.c_scale, xv = io.xv, qv = io.qv, tkv = io.tkv;
+  // The whole per-thread state lives in local memory across the out-of-line calls, and with two CTAs per SM the stacks do
+  // not fit L1: every first touch is an L2 round trip (~230 cycles; r2 profile: 40 % of the check's samples were
+  // long-scoreboard stalls at a dozen separate use sites).  Pull every field the check needs into registers in ONE run of
+  // loads behind a fence, so that the round trips overlap.
+  const int K = io.K;
+  const double c_scale = io.c_scale, xv = io.xv, qv = io.qv, tkv = io.tkv, io_f0 = io.f0, io_f1 = io.f1, io_f2 = io.f2;
   double rhobar = io.rhobar;
   int state = io.state;
   const int it = io.it;
   const int live = io.live;
-  double w[5], p[5], l[5], u[5], rho[5], er[5], ier[5], y[5], dy[5];
+  const int io_kj = io.kj;
+  double w[5], p[5], l[5], u[5], rho[5], er[5], ier[5], yo[5], ce[6], y[5], dy[5];
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     w[s] = io.w[s]; p[s] = io.p[s]; l[s] = io.l[s]; u[s] = io.u[s]; rho[s] = io.rho[s]; er[s] = io.er[s]; ier[s] = io.ier[s];
+    yo[s] = io.yo[s];
   }
+#pragma unroll
+  for (int m = 0; m < 6; m++) ce[m] = io.ce[m];
+  qpd_sched_fence();
   double red_v[QPD_NRED];
 #pragma unroll
   for (int r = 0; r < QPD_NRED; r++) red_v[r] = 0.0;
@@ -213,7 +223,7 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     y[s] = rho[s] * (w[s] - p[s]);
-    dy[s] = y[s] - io.yo[s];
+    dy[s] = y[s] - yo[s];
     const bool counted = ((live >> s) & 1) && (s < 4 || (live & 32));  // the redundant join copies count once
     if (counted && rho[s] > 0.0) {
       red_v[7] = qpd_max(red_v[7], fabs(c_scale * dy[s] * ier[s]));
@@ -222,8 +232,8 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
   }
   if (isvar) xr[QPD_CP + v] = xv;
   sync_cta();
-  const double atd = qpa_gather<true>(dy, lane, jsrc, tkv, io.f0, io.f1, io.f2, 0.0);
-  const double aty = qpa_gather<true>(y, lane, jsrc, tkv, io.f0, io.f1, io.f2, 0.0);
+  const double atd = qpa_gather<true>(dy, lane, jsrc, tkv, io_f0, io_f1, io_f2, 0.0);
+  const double aty = qpa_gather<true>(y, lane, jsrc, tkv, io_f0, io_f1, io_f2, 0.0);
   if (isvar) {
     const double cDv = seg < K ? lsx[QPD_LS * seg + 15 + i] : 0.0;
     double px = 0.0;
@@ -242,14 +252,14 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
   }
   {
     const double *cp = xr + QPD_CP + v;
-    const double *cpj = xr + QPD_CP + 6 * io.kj - 3;
+    const double *cpj = xr + QPD_CP + 6 * io_kj - 3;
     const double c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
     const double d1 = c1 - c0, e1 = c2 - c1, f1_ = c3 - c2;
     const double d2 = e1 - d1, e2 = f1_ - e1;
     const double d3 = e2 - d2;
     double ax[5];
     ax[0] = tkv * c0; ax[1] = 5.0 * d1; ax[2] = 20.0 * d2; ax[3] = 60.0 * d3;
-    ax[4] = (io.ce[0] * cpj[0] + io.ce[1] * cpj[1]) + (io.ce[2] * cpj[2] + io.ce[3] * cpj[3]) + (io.ce[4] * cpj[4] + io.ce[5] * cpj[5]);
+    ax[4] = (ce[0] * cpj[0] + ce[1] * cpj[1]) + (ce[2] * cpj[2] + ce[3] * cpj[3]) + (ce[4] * cpj[4] + ce[5] * cpj[5]);
 #pragma unroll
     for (int s = 0; s < 5; s++) {
       const bool counted = ((live >> s) & 1) && (s < 4 || (live & 32));
@@ -283,7 +293,7 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
         const bool counted = ((live >> s) & 1) && (s < 4 || (live & 32));
         if (counted) {
           const int r_old = s == 0 ? i : (s == 1 ? 6 + i : (s == 2 ? 11 + i : (s == 3 ? 15 + i : 18 + (i % 3))));
-          ctl_rho[r_old * STR + (s < 4 ? seg : io.kj)] = rn;
+          ctl_rho[r_old * STR + (s < 4 ? seg : io_kj)] = rn;
         }
       }
       rhobar = est;
@@ -366,7 +376,7 @@ SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       io.tkv = d[0]; io.qv = d[3 + i]; io.sigv = d[9 + i];
     }
   }
-  io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 1; io.it = 0;
+  io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 1; io.it = 0; io.K = K;
   sync_cta();
 
   // ---------------- ADMM, blocked by check interval ----------------

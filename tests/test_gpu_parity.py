@@ -122,8 +122,12 @@ def test_unchanged_reference_wrapper_reproduces_shipped_output(tmp_path, monkeyp
         assert np.abs(out[:, 1 + c] - gold[:, 1 + c]).max() <= tol[c]
     with open(os.path.join(REF_LIB_DIR, "weights.txt"), "w") as f:
         f.write("\t".join(str(v) for v in WEIGHTS_FILE) + "\n")
-    assert w.find_traj() is True   # the module's own entry: reads weights.txt, iteration = 3 (trp_wrapper.py:99-121)
-    assert os.path.exists(os.path.join(REF_LIB_DIR, "s1_slt_3d_3.txt" if trp else "s1_cub_3d_3.txt"))
+    own = os.path.join(REF_LIB_DIR, "s1_slt_3d_3.txt" if trp else "s1_cub_3d_1.txt")
+    if os.path.exists(own):
+        os.remove(own)
+    # the module's own entry: reads weights.txt; iteration = 3 in trp_wrapper.py:99-121, 1 in cub_wrapper.py:99-121
+    assert w.find_traj() is True
+    assert os.path.exists(own)
 
 
 def test_find_traj_failure_sentinel(tmp_path):

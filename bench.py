@@ -461,7 +461,7 @@ def run_sweep5(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    total = args.total
+    total = args.total if args.total > 0 else (262144 if args.config == 4 else 1048576)
     planner = api.SpectralPlanner(device=local, max_batch=sd.CHUNK, n_max=128, r_max=8, k_max=16)
     ident = [api.SpectralPlanner.comm_unique_id() if (rank == 0 and world > 1) else None]
     if world > 1:
@@ -540,8 +540,10 @@ def run_sweep5(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
                 "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "config5: %d-scenario sweep, config-4 generator (mixed trp+cub, K in [4,14], seed 20230603), contiguous "
-                                       "global-index shards over %d rank(s), one NCCL argmin exchange per pass (spectral_sweep_argmin)" % (total, world),
+                "config": {"workload": ("config4: mixed trp+cub batch of %d heterogeneous corridor sequences (K in [4,14], seed 20230603), variable-structure "
+                                        "ADMM path, %d rank(s), arg-min of the batch at the end (spectral_sweep_argmin)" if args.config == 4 else
+                                        "config5: %d-scenario sweep, config-4 generator (mixed trp+cub, K in [4,14], seed 20230603), contiguous "
+                                        "global-index shards over %d rank(s), one NCCL argmin exchange per pass (spectral_sweep_argmin)") % (total, world),
                            "total_scenarios": total, "chunk": sd.CHUNK, "scenarios_this_rank": n_local,
                            "l2": "inputs larger than L2: %.1f GB resident per rank" % (n_local * 8.1e3 / 1e9),
                            "winner": {"cost": winner["cost"], "index": winner["index"], "rank": winner["rank"], "K": winner["K"]},
@@ -567,15 +569,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pool", type=int, default=0, help="distinct batches resident per rank (0: the workload's default)")
     ap.add_argument("--streams", type=int, default=0, help="steps in flight (one handle + CUDA stream each; 0: the workload's default)")
-    ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA); 5: configs[4] (1 M sweep, strong scaling)")
-    ap.add_argument("--total", type=int, default=1048576, help="config 5: scenarios in the sweep (multiple of 8192)")
+    ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA); 4: configs[3] (262 144 mixed trp+cub, variable structure); 5: configs[4] (1 M sweep, strong scaling)")
+    ap.add_argument("--total", type=int, default=0, help="config 4 / 5: scenarios in the batch / sweep (multiple of 8192; default 262144 / 1048576)")
     ap.add_argument("--no-shared", action="store_true", help="config 3 through the per-scenario kernels (A/B of the shared-KKT path)")
     ap.add_argument("--groups", type=int, default=8, help="config 3: number of shared-KKT groups (1, 8, 64)")
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.config == 5:
+    elif args.config in (4, 5):
         run_sweep5(args)
     else:
         run_ours(args)

@@ -13,6 +13,8 @@
 // failure sentinel instead of computing on garbage; cub's uninitialised l_cost starts at 0; trp's
 // end-term reads the last available sample instead of out of bounds.
 // The numerical work happens on the GPU; there is no CPU path.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -138,7 +140,43 @@ extern "C" double find_traj(SpectralParams *p) {
     std::cerr << "Piecewise jerk speed optimizer failed!" << std::endl;  // trp_wrapper.cpp:197-199
     return kFail;
   }
-  if (verbose()) std::cout << "a_cost " << a_cost << std::endl;
+  if (verbose()) {
+    // the reference's remaining print blocks (trp_wrapper.cpp:116-132 refs, :217-239 s part, :243-280 l part): the same
+    // lines in the same order, with the cost terms accumulated on the host from the samples exactly as the reference
+    // does (the returned a_cost is the device's; the trp end term reads the last available sample)
+    std::cout << "\nx ref:\n";
+    for (int i = 0; i < N; i++) std::cout << sref[i] << " ";
+    std::cout << "\ny ref:\n";
+    for (int i = 0; i < N; i++) std::cout << lref[i] << " ";
+    std::cout << "\n\n";
+    const int np = npts < cap ? npts : cap;
+    for (int axis = 0; axis < 2; axis++) {
+      const int o = 3 * axis;
+      const double w_ref = w[axis == 0 ? 4 : 6], w_dref = w[axis == 0 ? 5 : 7], w_acc = w[axis == 0 ? 0 : 2], w_jerk = w[axis == 0 ? 1 : 3];
+      const std::vector<double> &ref = axis == 0 ? sref : lref;
+      double cost = 0.0, mmax_a = 0.0;
+      if (axis == 1) std::cout << "\n\n\nL part of trajectory: \n\n\n\n\nprinting L part: \n\nl size is\t" << np << "\n\n";
+      for (int i = 0; i < np; ++i) {
+        const double *q = &samples[(size_t)i * 6 + o];
+        const double dd_prev = i == 0 ? q[2] : samples[(size_t)(i - 1) * 6 + o + 2];
+        const double dd_next = (i == 0 && np > 1) ? samples[(size_t)6 + o + 2] : q[2];
+        const double ddd = (i == 0) ? (dd_next - q[2]) / delta_t : (q[2] - dd_prev) / delta_t;
+        const double r = i < N ? ref[i] : 0.0;
+        cost += w_ref * (q[0] - r) * (q[0] - r) * delta_t + w_dref * q[1] * q[1] * delta_t + w_acc * q[2] * q[2] * delta_t +
+                w_jerk * ddd * ddd * delta_t;
+        mmax_a = std::max(mmax_a, std::fabs(q[2]));
+        std::cout << std::fixed << std::setprecision(3) << "For t[" << i * delta_t << "], opt = " << q[0] << ", " << q[1] << ", " << q[2]
+                  << ", " << ddd << std::endl;
+      }
+      if (axis == 1 && np > 0 && SPECTRAL_VARIANT == SPECTRAL_TRP) {
+        const double e = samples[(size_t)(np - 1) * 6 + 3] - lref[np - 1 < N ? np - 1 : N - 1];
+        cost += w[9] * e * e * delta_t;
+      }
+      std::cout << (axis == 0 ? "\ns_cost is \t" : "\nl_cost is \t") << cost << "\n";
+      std::cout << "mmax_a " << mmax_a << std::endl;
+    }
+    std::cout << "a_cost " << a_cost << std::endl;
+  }
   std::string file = io_dir() + (SPECTRAL_VARIANT == SPECTRAL_TRP ? "/s1_slt_3d_" : "/s1_cub_3d_");
   file += std::to_string(p->iteration) + ".txt";
   std::ofstream ofs(file);

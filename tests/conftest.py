@@ -49,3 +49,32 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """One JSON line per parity check of the session (tests/helpers.assert_batch_parity) plus one aggregate line, in the
+    pytest output itself, so that the driver's log keeps the measured parity statistics: how many scenarios were compared
+    and how (KKT-verified optimum vs ADMM iterate), iteration-count agreement, class mismatches, exceptions."""
+    try:
+        import json
+        import helpers
+    except Exception:
+        return
+    log = helpers.PARITY_LOG
+    if not log:
+        return
+    tr = terminalreporter
+    tr.write_line("")
+    for s in log:
+        tr.write_line(json.dumps({"parity_stats": s}))
+    tot = lambda k: int(sum((s.get(k) or 0) for s in log))  # noqa: E731
+    it_c = tot("iters_compared")
+    it_eq = sum((s.get("iters_equal_frac") or 0.0) * (s.get("iters_compared") or 0) for s in log)
+    agg = {"checks": len(log), "scenarios": tot("B"), "decided": tot("decided"), "class_mismatch_decided": tot("class_mismatch_decided"),
+           "class_mismatch_undecided": tot("class_mismatch_undecided"), "both_solved": tot("both_solved"),
+           "compared_verified": tot("compared_verified"), "compared_iterate": tot("compared_iterate"), "exceptions": tot("exceptions"),
+           "charged_to_oracle": tot("charged_to_oracle"), "iterate_outliers": tot("iterate_outliers"), "iters_compared": it_c,
+           "iters_equal_frac": (it_eq / it_c) if it_c else None,
+           "verified_max_err_in_tol_units": max([s.get("verified_max_err_in_tol_units") or 0.0 for s in log]),
+           "iterate_max_err_in_tol_units": max([s.get("iterate_max_err_in_tol_units") or 0.0 for s in log])}
+    tr.write_line(json.dumps({"parity_summary": agg}))

@@ -28,7 +28,7 @@ static_assert(SPECTRAL_NUM_CLASSES == SP_NUM_CLASSES && SPECTRAL_NUM_WORK >= 6 +
 
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
 extern "C" int spectral_corridor_prepare(int N, int R, int *configured);                           // corridor.cu
-extern "C" void spectral_launch_bounds(const BoundsArgs &a, cudaStream_t st);                      // corridor.cu (same --fmad=false unit)
+extern "C" void spectral_launch_bounds(const BoundsArgs &a, int max_blocks, cudaStream_t st);      // corridor.cu (same --fmad=false unit)
 
 // ------------------------------------------------------------------ kernels
 __global__ void k_tables(const double *weights, double *mqm, int W) {
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(2 * QpdLayout<KC>::TA, 2) k_qpa(const QpArgs a
 
 // the step after the hot path (downstream.cuh)
 __global__ void k_ego_states(const double *samples, const int *npts, int cap, const double *s_offset, int off_stride, double *states, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x;
   if (b < B && i < cap) ego_state_body(samples, npts, cap, s_offset, off_stride, states, b, i);
 }
 __global__ void k_frenet_to_cartesian(const double *ref, const double *s_cond, const double *d_cond, double *out, long long n) {
@@ -834,7 +834,7 @@ extern "C" int spectral_bounds_device(spectral_handle_t *h, int B, int N, int M,
     return fail(h, SPECTRAL_ERR_CAPACITY, "bounds: shape exceeds the capacity (obstacles per scenario <= 4, lanes <= 24)");
   CK(cudaSetDevice(h->device));
   BoundsArgs a{B, N, M, R_cap, obstacles_dev, n_obs_dev, road[0], road[1], road[2], road[3], s_bounds_dev, l_bounds_dev, n_lanes_dev};
-  spectral_launch_bounds(a, (cudaStream_t)cuda_stream);
+  spectral_launch_bounds(a, 5 * h->sm_count, (cudaStream_t)cuda_stream);   // 40 KB of tables per CTA: five CTAs per SM, grid-stride
   h->launches++;
   CK(cudaGetLastError());
   return SPECTRAL_SUCCESS;
@@ -844,9 +844,8 @@ extern "C" int spectral_bounds_device(spectral_handle_t *h, int B, int N, int M,
 extern "C" int spectral_ego_states_device(spectral_handle_t *h, int B, const double *samples_dev, const int *npts_dev, int samples_cap,
                                           const double *s_offset_dev, int offset_stride, double *states_dev, void *cuda_stream) {
   if (!h || B <= 0 || samples_cap <= 0 || !samples_dev || !npts_dev || !s_offset_dev || !states_dev) return SPECTRAL_ERR_INVALID;
-  if (B > 65535) return fail(h, SPECTRAL_ERR_CAPACITY, "ego states: at most 65535 scenarios per call");
   CK(cudaSetDevice(h->device));
-  dim3 grid((samples_cap + 127) / 128, B);
+  dim3 grid(B, (samples_cap + 127) / 128);
   k_ego_states<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(samples_dev, npts_dev, samples_cap, s_offset_dev, offset_stride ? 1 : 0, states_dev, B);
   h->launches++;
   CK(cudaGetLastError());

@@ -38,9 +38,14 @@ extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st)
   k_corridor<<<a.B, 32 * a.R, L.total, st>>>(a);
 }
 
-// upstream bound generator (bounds.cuh): one warp per scenario, four scenarios per CTA
+// upstream bound generator (bounds.cuh): one warp per scenario, four warps per CTA, grid-stride over scenarios
 __global__ void __launch_bounds__(128) k_bounds(const BoundsArgs a) {
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b < a.B) bounds_warp_body(a, b, threadIdx.x & 31);
+  __shared__ SpbTable tables[4];
+  const int warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x * 4 + warp; b < a.B; b += gridDim.x * 4) bounds_warp_body(a, b, threadIdx.x & 31, &tables[warp]);
 }
-extern "C" void spectral_launch_bounds(const BoundsArgs &a, cudaStream_t st) { k_bounds<<<(a.B + 3) / 4, 128, 0, st>>>(a); }
+extern "C" void spectral_launch_bounds(const BoundsArgs &a, int max_blocks, cudaStream_t st) {
+  int blocks = (a.B + 3) / 4;
+  if (blocks > max_blocks) blocks = max_blocks;
+  k_bounds<<<blocks, 128, 0, st>>>(a);
+}

@@ -156,10 +156,11 @@ extern "C" void emu_default_options(SpectralOptions *o) {
   o->infeasibility_precheck = 0; o->precheck_margin = 1e-3; o->shared_kkt = 0;
 }
 
-// upstream bound generator (bounds.cuh): the warp body has no warp collectives, so the 32 lanes run one after the other
+// upstream bound generator (bounds.cuh): one emulated warp per scenario, the table in host memory
 extern "C" void emu_bounds(int B, int N, int M, int R_cap, const double *obstacles, const int *n_obs, const double *road, double *s_bounds,
                            double *l_bounds, int *n_lanes) {
   BoundsArgs a{B, N, M, R_cap, obstacles, n_obs, road[0], road[1], road[2], road[3], s_bounds, l_bounds, n_lanes};
+  std::vector<SpbTable> T(1);
   for (int b = 0; b < B; b++)
-    for (int lane = 0; lane < 32; lane++) bounds_warp_body(a, b, lane);
+    run_warps(1, [&](int, int lane, pthread_barrier_t *) { bounds_warp_body(a, b, lane, &T[0]); });
 }

@@ -162,6 +162,13 @@ def test_emu_bounds_kernel_random_obstacles_and_padding():
     n_over = H.assert_bounds_equal_oracle(sb, lb, nl, obs, n_obs, 71, 12)
     assert n_over < 100 and (nl > 0).sum() > 1900
     assert len(np.unique(nl)) >= 6
+    # capacity / argument edge cases: no obstacle, more obstacles than slots, more lanes than R_cap -> n_lanes = -1 and the
+    # whole output written as empty lanes (a solve on it reports "no corridor" instead of reading garbage)
+    sb, lb, nl = H.emu_bounds(obs[:3], [0, 5, int(n_obs[2])], 71, 12)
+    assert nl[0] == -1 and nl[1] == -1 and nl[2] > 0
+    assert np.all(lb[:2, :, :, 0] == 1.0) and np.all(lb[:2, :, :, 1] == -1.0) and np.all(sb[:2, :, :, 1] == 50.0)
+    sb, lb, nl = H.emu_bounds(obs[:64], n_obs[:64], 71, 2)
+    assert (nl == -1).sum() > 32 and np.all(lb[nl == -1][:, :, :, 0] == 1.0)
     # padding is inert for the corridor stage: fixture c1 (2 regions) padded with 3 empty lanes
     base = H.fixture_batch("c1")
     N = base.n_knots

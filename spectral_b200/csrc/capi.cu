@@ -22,13 +22,14 @@
 #include "qp_dense.cuh"
 #include "qp_anchor.cuh"
 #include "qp_shared.cuh"
+#include "qp_shared4.cuh"
 #include "tables.cuh"
 
 static_assert(SPECTRAL_NUM_CLASSES == SP_NUM_CLASSES && SPECTRAL_NUM_WORK >= 6 + SP_NUM_CLASSES, "include/spectral.h");
 
 extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st);  // corridor.cu
 extern "C" int spectral_corridor_prepare(int N, int R, int *configured);                           // corridor.cu
-extern "C" void spectral_launch_bounds(const BoundsArgs &a, int max_blocks, cudaStream_t st);      // corridor.cu (same --fmad=false unit)
+extern "C" int spectral_launch_bounds(const BoundsArgs &a, int sm_count, cudaStream_t st);         // corridor.cu (same --fmad=false unit)
 
 // ------------------------------------------------------------------ kernels
 __global__ void k_tables(const double *weights, double *mqm, int W) {
@@ -214,6 +215,24 @@ __global__ void __launch_bounds__(64) k_qps(const QpsArgs A) {
     __syncthreads();
   }
 }
+// four warps per tile (qp_shared4.cuh): warp = (axis, half), one segment per thread
+__global__ void __launch_bounds__(128, 2) k_qps4(const QpsArgs A) {
+  extern __shared__ __align__(16) double qps_smem[];
+  __shared__ int s_tile;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(A.tile_next, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    __syncthreads();
+    if (tile >= *A.n_tiles) return;
+    qps4_tile_body(A, tile, blockIdx.x, threadIdx.x, qps_smem, []() { __syncthreads(); },
+                   [](int axis) {  // named barrier over the 64 threads of one axis
+                     if (axis == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+                     else asm volatile("bar.sync 2, 64;" ::: "memory");
+                   });
+    __syncthreads();
+  }
+}
 __global__ void __launch_bounds__(64) k_qps_finish(const QpsArgs A) {
   extern __shared__ double qp_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -361,6 +380,7 @@ struct spectral_handle {
   int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
+  bool legacy_qps = false;  // SPECTRAL_LEGACY_QPS=1: the two-warp shared-KKT tile kernel instead of the four-warp one
 };
 
 static int fail(spectral_handle *h, int code, const std::string &msg) {
@@ -397,6 +417,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   spectral_handle *h = new spectral_handle();
   h->device = device; h->max_batch = max_batch; h->n_max = n_max; h->r_max = r_max; h->k_max = k_max;
   { const char *e = getenv("SPECTRAL_LEGACY_QPD"); h->legacy_qpd = e && e[0] == '1'; }
+  { const char *e = getenv("SPECTRAL_LEGACY_QPS"); h->legacy_qps = e && e[0] == '1'; }
   *out = h;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -564,10 +585,17 @@ static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, 
   CK(cudaFuncSetAttribute(k_qps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QpsSmem::BYTES));
   const int pf_blocks = (B + 3) / 4;  // two scenarios per warp, two warps per block
   k_qps_prepare<<<pf_blocks, 64, sm_pf, st>>>(A, h->qs_leader);
-  const int per_sm = 2 * (QpsSmem::BYTES + 1024 + 16) <= 227 * 1024 ? 2 : 1;
-  const int tiles_max = (B + 0) / 1;
-  const int grid = tiles_max < per_sm * h->sm_count ? tiles_max : per_sm * h->sm_count;
-  k_qps<<<grid, 64, QpsSmem::BYTES, st>>>(A);
+  const int tiles_max = B;
+  if (h->legacy_qps) {   // SPECTRAL_LEGACY_QPS=1: the two-warp tile layout (A/B measurements)
+    const int per_sm = 2 * (QpsSmem::BYTES + 1024 + 16) <= 227 * 1024 ? 2 : 1;
+    const int grid = tiles_max < per_sm * h->sm_count ? tiles_max : per_sm * h->sm_count;
+    k_qps<<<grid, 64, QpsSmem::BYTES, st>>>(A);
+  } else {
+    CK(cudaFuncSetAttribute(k_qps4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Qps4Smem::BYTES));
+    const int per_sm = 2 * (Qps4Smem::BYTES + 1024 + 16) <= 227 * 1024 ? 2 : 1;
+    const int grid = tiles_max < per_sm * h->sm_count ? tiles_max : per_sm * h->sm_count;
+    k_qps4<<<grid, 128, Qps4Smem::BYTES, st>>>(A);
+  }
   k_qps_finish<<<pf_blocks, 64, sm_pf, st>>>(A);
   h->launches += 8;
   CK(cudaGetLastError());
@@ -834,7 +862,7 @@ extern "C" int spectral_bounds_device(spectral_handle_t *h, int B, int N, int M,
     return fail(h, SPECTRAL_ERR_CAPACITY, "bounds: shape exceeds the capacity (obstacles per scenario <= 4, lanes <= 24)");
   CK(cudaSetDevice(h->device));
   BoundsArgs a{B, N, M, R_cap, obstacles_dev, n_obs_dev, road[0], road[1], road[2], road[3], s_bounds_dev, l_bounds_dev, n_lanes_dev};
-  spectral_launch_bounds(a, 5 * h->sm_count, (cudaStream_t)cuda_stream);   // 40 KB of tables per CTA: five CTAs per SM, grid-stride
+  if (spectral_launch_bounds(a, h->sm_count, (cudaStream_t)cuda_stream) != 0) return fail(h, SPECTRAL_ERR_CUDA, "bounds kernel: shared memory opt-in failed");
   h->launches++;
   CK(cudaGetLastError());
   return SPECTRAL_SUCCESS;

@@ -38,14 +38,22 @@ extern "C" void spectral_launch_corridor(const CorridorArgs &a, cudaStream_t st)
   k_corridor<<<a.B, 32 * a.R, L.total, st>>>(a);
 }
 
-// upstream bound generator (bounds.cuh): one warp per scenario, four warps per CTA, grid-stride over scenarios
-__global__ void __launch_bounds__(128) k_bounds(const BoundsArgs a) {
-  __shared__ SpbTable tables[4];
+// upstream bound generator (bounds.cuh): one warp per scenario, four warps per CTA, grid-stride over scenarios.  Per warp
+// a lane table + a [4][N] line cache in dynamic shared memory (3.6 KB at N = 71), registers capped for 8 CTAs per SM: the
+// kernel is latency-bound (sequential table logic, IEEE divisions), so resident warps are what it needs.
+__global__ void __launch_bounds__(128, 8) k_bounds(const BoundsArgs a) {
+  extern __shared__ __align__(16) unsigned char bounds_smem[];
   const int warp = threadIdx.x >> 5;
-  for (int b = blockIdx.x * 4 + warp; b < a.B; b += gridDim.x * 4) bounds_warp_body(a, b, threadIdx.x & 31, &tables[warp]);
+  unsigned char *mine = bounds_smem + (size_t)warp * ((spb_smem_bytes_per_warp(a.N) + 15) / 16 * 16);
+  SpbTable *T = reinterpret_cast<SpbTable *>(mine);
+  double *line = reinterpret_cast<double *>(mine + sizeof(SpbTable));
+  for (int b = blockIdx.x * 4 + warp; b < a.B; b += gridDim.x * 4) bounds_warp_body(a, b, threadIdx.x & 31, T, line);
 }
-extern "C" void spectral_launch_bounds(const BoundsArgs &a, int max_blocks, cudaStream_t st) {
+extern "C" int spectral_launch_bounds(const BoundsArgs &a, int sm_count, cudaStream_t st) {
+  const size_t smem = 4 * ((spb_smem_bytes_per_warp(a.N) + 15) / 16 * 16);
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(k_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int blocks = (a.B + 3) / 4;
-  if (blocks > max_blocks) blocks = max_blocks;
-  k_bounds<<<blocks, 128, 0, st>>>(a);
+  if (blocks > 8 * sm_count) blocks = 8 * sm_count;
+  k_bounds<<<blocks, 128, smem, st>>>(a);
+  return 0;
 }

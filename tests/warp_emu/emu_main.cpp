@@ -161,6 +161,7 @@ extern "C" void emu_bounds(int B, int N, int M, int R_cap, const double *obstacl
                            double *l_bounds, int *n_lanes) {
   BoundsArgs a{B, N, M, R_cap, obstacles, n_obs, road[0], road[1], road[2], road[3], s_bounds, l_bounds, n_lanes};
   std::vector<SpbTable> T(1);
+  std::vector<double> line((size_t)SPB_MAX_CARS * N);
   for (int b = 0; b < B; b++)
-    run_warps(1, [&](int, int lane, pthread_barrier_t *) { bounds_warp_body(a, b, lane, &T[0]); });
+    run_warps(1, [&](int, int lane, pthread_barrier_t *) { bounds_warp_body(a, b, lane, &T[0], line.data()); });
 }

@@ -178,8 +178,10 @@ SP_DEV_NOINLINE void qpa_block(QpaIO<6 * KC> &io, double *smx, int ta, int axis_
 
 // OSQP's termination test / primal-infeasibility certificate / adaptive-rho rule, CTA-wide (= jointly over the s and l
 // problems), in the anchor layout.  Same quantities as qpd_check.
+// Returns state | need_g << 8 (the caller keeps both in registers: reading them back from the state block costs an L2 round
+// trip per block of iterations).
 template <int KC, typename SyncFn>
-SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem, QpaIO<6 * KC> &io, SyncFn sync_cta) {
+SP_DEV_NOINLINE int qpa_check(const QpArgs &a, int slot, int tid, double *smem, QpaIO<6 * KC> &io, SyncFn sync_cta) {
   using L = QpdLayout<KC>;
   constexpr int STR = L::STR, TA = L::TA;
   const SpOptionsDev &o = a.opt;
@@ -202,7 +204,7 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
   const int K = io.K;
   const double c_scale = io.c_scale, xv = io.xv, qv = io.qv, tkv = io.tkv, io_f0 = io.f0, io_f1 = io.f1, io_f2 = io.f2;
   double rhobar = io.rhobar;
-  int state = io.state;
+  int state = io.state, need_g = 0;
   const int it = io.it;
   const int live = io.live;
   const int io_kj = io.kj;
@@ -301,11 +303,12 @@ SP_DEV_NOINLINE void qpa_check(const QpArgs &a, int slot, int tid, double *smem,
       if (warp == 0) qpd_control_refactor<KC>(a, slot, lane, smem, c_scale, rhobar);
       sync_cta();
       if (red[0] != 0.0) state = QP_ST_INFEASIBLE;
-      io.need_g = 1;
+      need_g = 1;
     }
   }
   io.rhobar = rhobar;
   io.state = state;
+  return state | (need_g << 8);
 }
 
 // slot: index of the scenario in this class' list.  tid in [0, 2 TA).  smem: QpdLayout<KC>::BYTES, 16-byte aligned.
@@ -376,16 +379,17 @@ SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       io.tkv = d[0]; io.qv = d[3 + i]; io.sigv = d[9 + i];
     }
   }
-  io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 1; io.it = 0; io.K = K;
+  io.c_scale = c_scale; io.rhobar = rhobar; io.state = state; io.need_g = 0; io.it = 0; io.K = K;
   sync_cta();
 
   // ---------------- ADMM, blocked by check interval ----------------
   int iters = 0;
   int it = 1;
-  while (it <= o.max_iter && io.state == QP_RUNNING) {
-    if (io.need_g) {
+  int need_g = 1;
+  while (it <= o.max_iter && state == QP_RUNNING) {
+    if (need_g) {
       qpd_build_g<KC>(smx + L::O_FS, v, 0, isvar, io.G);
-      io.need_g = 0;
+      need_g = 0;
     }
     int it_end = o.max_iter;
     if (o.check_every > 0) {
@@ -403,9 +407,10 @@ SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
     it = it_end + 1;
     if (!check) continue;
     io.it = iters;
-    qpa_check<KC>(a, slot, tid, smem, io, sync_cta);  // (the axes ran the block independently; the check's barriers are CTA-wide)
+    const int r = qpa_check<KC>(a, slot, tid, smem, io, sync_cta);  // (the axes ran the block independently; the check's barriers are CTA-wide)
+    state = r & 0xff;
+    need_g = r >> 8;
   }
-  state = io.state;
   rhobar = io.rhobar;
 
   // ---------------- hand the iterate back to the lane-per-segment layout: W slots, rho, x ----------------

@@ -15,10 +15,14 @@ value : whole-job solves/s with the inputs already resident in HBM (CUDA events,
         L2 hygiene: the step rotates through a pool of distinct batches whose inputs + outputs exceed the
         126 MB L2 ("inputs larger than L2").
 e2e   : same metric through spectral_solve_batch() with HOST buffers (pinned), H2D + D2H inside the timed region.
-roofline      : the dominant kernel (k_qp, batched ADMM): algorithmic FP64 flops / its CUDA-event time vs the
-                FP64 FMA peak measured on this device by the library's probe kernel; plus `roofline_corridor`,
-                the HBM-bound corridor kernel, against MEASURED_PEAKS.json.
+roofline      : the dominant kernel (k_qpa / k_qpd, batched ADMM; k_qps4 with --config 3): algorithmic FP64 flops / its
+                CUDA-event time vs the FP64 FMA peak measured on this device by the library's probe kernel, per solver
+                class too; plus `roofline_corridor` (the corridor kernel) and `roofline_side_kernels` (k_bounds and the
+                downstream kernels) against the HBM copy bandwidth of MEASURED_PEAKS.json.
 cpu_baseline  : the reference's own sources (oracle/_ref, OSQP restated) on all host cores, bounded sample.
+Other workloads (supplementary lines, same JSON shape): --config 3 (BASELINE configs[2]: 65 536 shared-KKT variants on the
+FP64 tensor cores, --groups 1|8|64), --config 4 (configs[3]: 262 144 mixed trp + cub), --config 5 (configs[4]: the 1 M-scenario
+sweep, strong scaling, NCCL arg-min through the C-ABI).
 """
 import argparse
 import json

@@ -1,7 +1,7 @@
 // spectral_b200/csrc/qp_shared4.cuh -- K4a, second layout: the shared-KKT tile kernel with FOUR warps per tile.
 //
-// Same algorithm, same tile builder, same prepare / finish kernels and the same shared-memory footprint as qp_shared.cuh
-// (read that header first); only the thread map of the tile body changes.  The two-warp layout (one warp per axis, two
+// Same algorithm, same tile builder and the same prepare / finish kernels as qp_shared.cuh (read that header first); only the
+// thread map of the tile body changes (and with it where the w rows live: registers here, shared memory there).  The two-warp layout (one warp per axis, two
 // segments per thread) is bound by shared-memory CAPACITY, not by any pipe: 110 KB per tile -> two tiles = four warps per SM,
 // one warp per scheduler, every dependent-instruction latency exposed (profiles/r2_qps_full.md: sm__warps_active 5.6 %,
 // stall "wait" 2.2 per issue).  Here one tile = 4 warps = (axis, half): lane 4n + q of warp (axis, h) owns ONE segment,

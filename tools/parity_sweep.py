@@ -31,11 +31,21 @@ bad = 0
 for variant, batch, w, name in cases:
     t = time.time()
     got = p.solve(variant, batch, w)
+    got0 = p.solve(variant, batch, w, options=api.default_options(polish=0))   # the reference's polish = 0: the raw ADMM iterate
     ref, ref0 = H.oracle_pair(variant, batch, w)
     try:
-        both = H.assert_batch_parity(got, ref, name, need_verified_frac=0.4, ref0=ref0, batch=batch, variant=variant, weights=w)
+        both = H.assert_batch_parity(got, ref, name, need_verified_frac=0.4, ref0=ref0, batch=batch, variant=variant, weights=w, got0=got0)
         print("%-20s B=%4d ok %4d verified %4d compared %4d  PASS  (%.0f s)" % (name, batch.batch, got.ok().sum(), got.verified().sum(), both.sum(), time.time() - t))
     except AssertionError as e:
         bad += 1
         print("%-20s FAIL: %s" % (name, str(e)[:300]))
 print("failures:", bad)
+import json
+log = H.PARITY_LOG
+tot = lambda k: int(sum((d.get(k) or 0) for d in log))  # noqa: E731
+itc = tot("iters_compared")
+print(json.dumps({"parity_sweep_summary": {"batches": len(cases), "failures": bad, "scenarios": tot("B"), "decided": tot("decided"),
+      "class_mismatch_decided": tot("class_mismatch_decided"), "class_mismatch_undecided": tot("class_mismatch_undecided"),
+      "iters_compared": itc, "iters_equal": int(round(sum((d.get("iters_equal_frac") or 0) * (d.get("iters_compared") or 0) for d in log))),
+      "compared_verified": tot("compared_verified"), "compared_iterate": tot("compared_iterate"), "iterate_outliers": tot("iterate_outliers"),
+      "exceptions": tot("exceptions"), "charged_to_oracle": tot("charged_to_oracle")}}))

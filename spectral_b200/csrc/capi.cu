@@ -380,6 +380,7 @@ struct spectral_handle {
   int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
+  bool force_lanes = false; // SPECTRAL_FORCE_LANES=1: k_qp<8|16> (lane per segment, block-tridiagonal solve) for every class
   bool legacy_qps = false;  // SPECTRAL_LEGACY_QPS=1: the two-warp shared-KKT tile kernel instead of the four-warp one
 };
 
@@ -418,6 +419,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   h->device = device; h->max_batch = max_batch; h->n_max = n_max; h->r_max = r_max; h->k_max = k_max;
   { const char *e = getenv("SPECTRAL_LEGACY_QPD"); h->legacy_qpd = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_LEGACY_QPS"); h->legacy_qps = e && e[0] == '1'; }
+  { const char *e = getenv("SPECTRAL_FORCE_LANES"); h->force_lanes = e && e[0] == '1'; }
   *out = h;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -696,7 +698,11 @@ static int solve_device_impl(spectral_handle_t *h, int variant, int B, int N, in
     qa.list = h->lists + (size_t)cls * B; qa.count = h->counts + cls; qa.next = h->counts + SP_NUM_CLASSES + cls;
     cudaEvent_t *ec = h->ev_cls[h->timed_calls % spectral_handle::kTimingSlots][cls];
     if (tm) CK(cudaEventRecord(ec[0], cs));
-    if (cls == 0 && opt.shared_kkt) { const int rc = launch_qps(h, qa, h->cstatus, B, in, cs); if (rc) return rc; }
+    if (h->force_lanes && cls < 4) {   // SPECTRAL_FORCE_LANES=1: lane-per-segment kernels for every class (A/B measurements)
+      if (cls == 0) CK((launch_qp<8, 2>(h, qa, B, cs)));
+      else CK((launch_qp<16, 2>(h, qa, B, cs)));
+    }
+    else if (cls == 0 && opt.shared_kkt) { const int rc = launch_qps(h, qa, h->cstatus, B, in, cs); if (rc) return rc; }
     else if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
     else if (cls == 1) CK((h->legacy_qpd ? launch_qpd<10>(h, qa, B, cs) : launch_qpa<10>(h, qa, B, cs)));
     else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));

@@ -751,6 +751,89 @@ SP_DEV void qp_setup(const QpArgs &a, int ap, bool have, int seg, int lane, doub
   (void)b; (void)axis; (void)K; (void)seg; (void)kmaxw; (void)have; (void)active; (void)first; (void)last; \
   (void)t; (void)tp; (void)tn; (void)c; (void)eqmask; (void)q; (void)sig; (void)cD
 
+// A block of `n` ADMM iterations WITHOUT a termination check, fused so that every iteration makes ONE pass over the lane's
+// 21 rows: the row update of iteration i (w += alpha (z~ - clip(w))) and the gather input of iteration i + 1
+// (v = rho (2 clip(w') - w')) come from the same loads.  Same arithmetic per quantity as the general iteration of
+// qp_admm_lanes below (which handles iteration 1, the check iterations and the rho updates), so the two can be interleaved.
+// Rows are staged in groups of CH (loads, arithmetic, stores) to bound the live registers next to the factor.
+#ifndef QP_FAST_BLOCK
+#define QP_FAST_BLOCK 1
+#endif
+SP_DEV double qp_ld(const double *p) {
+#ifdef SPECTRAL_CPU_EMU
+  return *p;
+#else
+  double a;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return a;
+#endif
+}
+template <int LPA, int STR, int RB, int RE, int CH, bool FIRST>
+SP_DEV void qp_fast_rows(double *sm, int lane, const double z[QP_ROWS], double alpha_eff, double v[QP_ROWS]) {
+  static_assert((RE - RB) % CH == 0, "whole groups");
+#pragma unroll
+  for (int r0 = RB; r0 < RE; r0 += CH) {
+    double w[CH], l[CH], u[CH], rh[CH];
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      w[j] = qp_ld(sm + (QP_SM_W + r0 + j) * STR + lane); l[j] = qp_ld(sm + (QP_SM_L + r0 + j) * STR + lane);
+      u[j] = qp_ld(sm + (QP_SM_U + r0 + j) * STR + lane); rh[j] = qp_ld(sm + (QP_SM_RHO + r0 + j) * STR + lane);
+    }
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      const int r = r0 + j;
+      if (FIRST) {   // block entry: only the gather input of the first iteration
+        const double p = fmin(fmax(w[j], l[j]), u[j]);
+        v[r] = rh[j] * (2.0 * p - w[j]);
+      } else {
+        const double p = fmin(fmax(w[j], l[j]), u[j]);
+        const double wn = w[j] + alpha_eff * (z[r] - p);
+        const double pn = fmin(fmax(wn, l[j]), u[j]);
+        v[r] = rh[j] * (2.0 * pn - wn);
+        w[j] = wn;
+      }
+    }
+    if (!FIRST) {
+#pragma unroll
+      for (int j = 0; j < CH; j++) sm[(QP_SM_W + r0 + j) * STR + lane] = w[j];
+    }
+  }
+}
+template <int LPA, int STR>
+SP_DEV void qp_fast_block(double *sm, int lane, const QpFactor &F, double x[6], const double q[6], const double sig[6], double t, double tp,
+                          double tn, bool first, bool last, int seg, int kmaxw, double alpha, bool run, int n) {
+  const double alpha_eff = run ? alpha : 0.0;   // a finished lane keeps its state
+  double g[6];
+  {
+    double v[QP_ROWS];
+    qp_fast_rows<LPA, STR, 0, 21, 7, true>(sm, lane, v, 0.0, v);
+    double n18 = sp_shfl_down(v[18], 1, LPA), n19 = sp_shfl_down(v[19], 1, LPA), n20 = sp_shfl_down(v[20], 1, LPA);
+    if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
+    apply_AT(v, n18, n19, n20, t, tp, tn, first, g);
+#pragma unroll
+    for (int j = 0; j < 6; j++) g[j] += sig[j] * x[j] - q[j];
+  }
+  for (int i = 0; i < n; i++) {
+    double xt[6];
+    qp_solve<LPA>(F, g, xt, seg, last, kmaxw);
+    if (run) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) x[j] = alpha * xt[j] + (1.0 - alpha) * x[j];
+    }
+    double v[QP_ROWS];
+    {
+      double p3 = sp_shfl_up(xt[3], 1, LPA), p4 = sp_shfl_up(xt[4], 1, LPA), p5 = sp_shfl_up(xt[5], 1, LPA);
+      apply_A(xt, p3, p4, p5, t, tp, first, v);  // v holds z_tilde ...
+    }
+    qp_fast_rows<LPA, STR, 0, 21, 7, false>(sm, lane, v, alpha_eff, v);   // ... and then rho (2 clip(w') - w') row by row
+    double n18 = sp_shfl_down(v[18], 1, LPA), n19 = sp_shfl_down(v[19], 1, LPA), n20 = sp_shfl_down(v[20], 1, LPA);
+    if (last) { n18 = 0.0; n19 = 0.0; n20 = 0.0; }
+    apply_AT(v, n18, n19, n20, t, tp, tn, first, g);
+#pragma unroll
+    for (int j = 0; j < 6; j++) g[j] += sig[j] * x[j] - q[j];
+  }
+}
+
 // The lane-per-segment ADMM loop (OSQP iteration in w form) with the factor F in registers.
 // Used by k_qp (segment counts above the dense kernel's capacity) and as the kernel-logic reference of
 // the dense loop in qp_dense.cuh.
@@ -774,6 +857,20 @@ SP_DEV void qp_admm_lanes(const SpOptionsDev &o, double *sm, int lane, QpLane &Q
     if (sp_all(state != QP_RUNNING)) break;
     const bool run = state == QP_RUNNING;
     const bool check = (o.check_every > 0) && (it % o.check_every == 0);
+#if QP_FAST_BLOCK
+    if (it > 1 && !check) {
+      // the iterations up to (not including) the next check, or to max_iter: the state cannot change inside the block
+      int it_end = o.max_iter + 1;
+      if (o.check_every > 0) {
+        const int nxt = (it / o.check_every + 1) * o.check_every;
+        it_end = nxt < it_end ? nxt : it_end;
+      }
+      qp_fast_block<LPA, STR>(sm, lane, F, x, q, sig, t, tp, tn, first, last, seg, kmaxw, alpha, run, it_end - it);
+      if (run) iters = it_end - 1;
+      it = it_end - 1;
+      continue;
+    }
+#endif
     double v[QP_ROWS];
     // v = rho (2 clip(w) - w)  (= rho z - y); first iteration: z = y = 0 exactly as OSQP's cold start
 #pragma unroll

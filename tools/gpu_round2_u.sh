@@ -1,0 +1,15 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+for st in 4 8; do
+SPECTRAL_FORCE_LANES=1 timeout 300 python bench.py --steps 40 --warmup 5 --streams $st > gpurun_out/u_lanes_s$st.json 2> gpurun_out/u_lanes_s$st.err; tail -c 200 gpurun_out/u_lanes_s$st.err
+done
+python - <<'PY'
+import json
+for st in (4,8):
+    try:
+        d=json.loads(open("gpurun_out/u_lanes_s%d.json"%st).read().strip().splitlines()[-1])
+        print("lanes streams",st,"value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "qp ms", d["kernel_ms_per_step"]["qp"], [ (c["class"], round(c["ms_per_step"],1)) for c in d["roofline"]["per_class"]])
+    except Exception as e: print(st,"ERR",e)
+PY
+SPECTRAL_FORCE_LANES=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "config2_cub" 2>&1 | tail -3 | cut -c1-300

@@ -30,6 +30,7 @@ struct CorridorSmem {
   int slab;       // bytes of one (lo,hi) slab: 16*N
   int off_xb;     // R slabs
   int off_yb;     // R slabs
+  int off_slope;  // R * 2 * N doubles: backward slopes of the lower / upper s-bound per knot (computed once per region)
   int off_cubes;  // R * SP_REGION_CAP cubes
   int off_cnt;    // R * SP_REGION_CAP ints
   int off_ncube;  // SP_MAX_REGIONS ints
@@ -47,6 +48,7 @@ SP_HD CorridorSmem corridor_smem_layout(int N, int R) {
   L.slab = 16 * N;
   L.off_xb = o; o += R * L.slab;
   L.off_yb = o; o += R * L.slab;
+  L.off_slope = o; o += R * L.slab;
   L.off_cubes = o; o += R * SP_REGION_CAP * (int)sizeof(SpectralCube);
   L.off_cnt = o; o += R * SP_REGION_CAP * 4;
   L.off_ncube = o; o += SP_MAX_REGIONS * 4;
@@ -229,9 +231,14 @@ SP_DEV void std_sort_by_beg_t(SortView v, int n) {
   } else ss_insertion_sort(v, 0, n);
 }
 
+// num / delta, IEEE.  A zero numerator (flat bounds: the common case) gives a zero of the numerator's sign for any
+// positive delta; answering it directly keeps the division's slow path (taken for zero operands) out of the way.
+SP_DEV double slope_div(double num, double delta) { return (num == 0.0 && delta > 0.0) ? num : num / delta; }
+
 // ---------------------------------------------------------------------------------------------
 // K1: one warp, one region.  Returns the cube count written to `out` (shared) or -1 (capacity).
-SP_DEV int corridor_generate_region(int variant, int N, double delta, const double *xb, const double *yb,
+// `slope`: 2 N doubles of shared memory for this region.
+SP_DEV int corridor_generate_region(int variant, int N, double delta, const double *xb, const double *yb, double *slope,
                                     SpectralCube *out, int lane) {
 #define XLO(i) xb[2 * (i)]
 #define XHI(i) xb[2 * (i) + 1]
@@ -241,15 +248,23 @@ SP_DEV int corridor_generate_region(int variant, int N, double delta, const doub
   SpectralCube mine;
   cube_defaults(mine);
   int j = 0;
-  double cur_down = (XLO(1) - XLO(0)) / delta;  // :332
-  double cur_up = (XHI(1) - XHI(0)) / delta;    // :334
+  // backward slopes of every knot, once (:355-356; the forward slope at a break knot i, :380-384, is the backward slope
+  // of knot i + 1: same operands, same operation).  The break search below then only compares.
+  double *dsk = slope, *usk = slope + N;
+  for (int i = 1 + lane; i < N; i += 32) {
+    dsk[i] = slope_div(XLO(i) - XLO(i - 1), delta);
+    usk[i] = slope_div(XHI(i) - XHI(i - 1), delta);
+  }
+  sp_syncwarp();
+  double cur_down = dsk[1];  // :332
+  double cur_up = usk[1];    // :334
   if (lane == 0) {
     mine.beg_t = 0;
     mine.down_skew = cur_down; mine.down_bias = XLO(0);
     mine.upp_skew = cur_up; mine.upp_bias = XHI(0);
     if (variant == SPECTRAL_TRP) {  // :338-341
-      mine.l_down_skew = (YLO(1) - YLO(0)) / delta; mine.l_down_bias = YLO(0);
-      mine.l_upp_skew = (YHI(1) - YHI(0)) / delta; mine.l_upp_bias = YHI(0);
+      mine.l_down_skew = slope_div(YLO(1) - YLO(0), delta); mine.l_down_bias = YLO(0);
+      mine.l_upp_skew = slope_div(YHI(1) - YHI(0), delta); mine.l_upp_bias = YHI(0);
     }
     mine.beg_l = YLO(0); mine.end_l = YHI(0);
   }
@@ -262,11 +277,7 @@ SP_DEV int corridor_generate_region(int variant, int N, double delta, const doub
     for (int base = i0; base <= N - 2; base += 32) {
       int i = base + lane;
       int pred = 0;
-      if (i <= N - 2) {
-        double dskew = (XLO(i) - XLO(i - 1)) / delta;
-        double uskew = (XHI(i) - XHI(i - 1)) / delta;
-        pred = (fabs(dskew - cur_down) > 0.2) || (fabs(uskew - cur_up) > 0.2);
-      }
+      if (i <= N - 2) pred = (fabs(dsk[i] - cur_down) > 0.2) || (fabs(usk[i] - cur_up) > 0.2);
       unsigned m = sp_ballot(pred);
       if (m) { found = base + sp_ffs(m) - 1; break; }
     }
@@ -274,16 +285,16 @@ SP_DEV int corridor_generate_region(int variant, int N, double delta, const doub
     if (j >= 32) { overflow = 1; break; }
     const int i = found;
     if (lane == j - 1) mine.end_t = i;  // :376
-    cur_down = (XLO(i + 1) - XLO(i)) / delta;  // :380
-    cur_up = (XHI(i + 1) - XHI(i)) / delta;    // :384
+    cur_down = dsk[i + 1];  // :380
+    cur_up = usk[i + 1];    // :384
     if (lane == j) {
       mine.beg_t = i;
       mine.down_skew = cur_down; mine.down_bias = XLO(i);
       mine.upp_skew = cur_up; mine.upp_bias = XHI(i);
       if (variant == SPECTRAL_TRP) {  // :360-367, backward differences at the break knot
         mine.l_down_bias = YLO(i); mine.l_upp_bias = YHI(i);
-        mine.l_down_skew = (YLO(i) - YLO(i - 1)) / delta;
-        mine.l_upp_skew = (YHI(i) - YHI(i - 1)) / delta;
+        mine.l_down_skew = slope_div(YLO(i) - YLO(i - 1), delta);
+        mine.l_upp_skew = slope_div(YHI(i) - YHI(i - 1), delta);
       }
       mine.beg_l = YLO(i); mine.end_l = YHI(i);  // :388-389
     }
@@ -345,6 +356,7 @@ SP_DEV void corridor_cta_body(const CorridorArgs &a, int b, int warp, int lane, 
   const CorridorSmem L = corridor_smem_layout(N, R);
   double *xb = (double *)(smem + L.off_xb + warp * L.slab);
   double *yb = (double *)(smem + L.off_yb + warp * L.slab);
+  double *slope = (double *)(smem + L.off_slope + warp * L.slab);
   SpectralCube *cubes = (SpectralCube *)(smem + L.off_cubes) + warp * SP_REGION_CAP;
   int *cnt = (int *)(smem + L.off_cnt) + warp * SP_REGION_CAP;
   int *ncube = (int *)(smem + L.off_ncube);
@@ -380,7 +392,7 @@ SP_DEV void corridor_cta_body(const CorridorArgs &a, int b, int warp, int lane, 
   sp_syncwarp();
 #endif
 
-  int n = corridor_generate_region(a.variant, N, a.delta, xb, yb, cubes, lane);
+  int n = corridor_generate_region(a.variant, N, a.delta, xb, yb, slope, cubes, lane);
   if (lane == 0) ncube[warp] = n;
   sync_cta();  // cubes + refs visible
 
@@ -388,11 +400,19 @@ SP_DEV void corridor_cta_body(const CorridorArgs &a, int b, int warp, int lane, 
   if (n > 0) {
     for (int k = 0; k < n; k++) {
       const SpectralCube c = cubes[k];
+      // The first and the third edge test of point_inside are  -(t - beg_t) a1  and  -(t - end_t) a3  (their other terms are
+      // multiplied by the reference's (beg_t - beg_t) / (end_t - end_t) = 0).  With a1 > 0 and a3 < 0 -- every cube whose upper
+      // face lies above its lower face -- they have strictly opposite signs for every knot outside [beg_t, end_t], i.e. such
+      // a knot is never inside: only the cube's own knots need the test.  Other cubes take the full scan.
+      const double a1 = c.upp_bias - c.down_bias;
+      const double a3 = c.down_skew * a.delta + c.down_bias - c.upp_skew * a.delta - c.upp_bias;
+      const bool local = a1 > 0.0 && a3 < 0.0 && c.beg_t >= 0 && c.end_t >= c.beg_t && c.end_t < N;
+      const int lo = local ? c.beg_t : 0, hi = local ? c.end_t + 1 : N;
       int total = 0;
-      for (int base = 0; base < N; base += 32) {
+      for (int base = lo; base < hi; base += 32) {
         int i = base + lane;
         int in = 0;
-        if (i < N) in = point_inside(c, sref[i], lref[i], (double)i, a.delta);
+        if (i < hi) in = point_inside(c, sref[i], lref[i], (double)i, a.delta);
         total += sp_popc(sp_ballot(in));
       }
       if (lane == 0) cnt[k] = total;

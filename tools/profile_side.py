@@ -23,6 +23,17 @@ inp["weights"] = torch.tensor(GOLDEN_W_CUB, dtype=torch.float64, device=dev)
 outs = p.alloc_device_outputs(B, samples_cap=72)
 opt = api.default_options(max_iter=50, polish=0)   # the solver kernels are not what this run is for
 p.solve_device("cub", 71, 2, 0.1, inp, outs, options=opt)
+torch.cuda.synchronize()
+p.set_timing(True)
+for _ in range(3):
+    p.solve_device("cub", 71, 2, 0.1, inp, outs, options=opt)
+torch.cuda.synchronize()
+kt = p.get_timing()
+calls = max(kt.get("calls", 1), 1)
+cor_ms = kt["corridor"] / calls
+cor_bytes = B * (8 * (4 * 2 * 71 + 2 * 71) + 4) + 112 * float(outs["K"].double().sum())
+print("k_corridor %.4f ms per %d scenarios, %.1f GB/s algorithmic (%.3f of 6420.7)" % (cor_ms, B, cor_bytes / cor_ms / 1e6, cor_bytes / cor_ms / 1e6 / 6420.7))
+p.set_timing(False)
 c = torch.zeros(1, dtype=torch.float64, device=dev); i = torch.zeros(1, dtype=torch.int64, device=dev)
 p.argmin_device(outs["a_cost"], 0, c, i)
 p.ego_states_device(outs["samples"], outs["npts"], torch.zeros(1, dtype=torch.float64, device=dev))

@@ -476,6 +476,8 @@ def run_sweep5(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     total = args.total if args.total > 0 else (262144 if args.config == 4 else 1048576)
+    # --shared: the K <= 8 class of every chunk through structure-sorted shared-KKT tiles (k_qps4); default: per-scenario kernels
+    sweep_opt = api.default_options(shared_kkt=1) if args.shared else None
     planner = api.SpectralPlanner(device=local, max_batch=sd.CHUNK, n_max=128, r_max=8, k_max=16)
     ident = [api.SpectralPlanner.comm_unique_id() if (rank == 0 and world > 1) else None]
     if world > 1:
@@ -494,7 +496,7 @@ def run_sweep5(args):
 
     winner = None
     for _ in range(max(1, args.warmup)):
-        winner = sd.run_sweep(planner, shard, outs)
+        winner = sd.run_sweep(planner, shard, outs, options=sweep_opt)
     barrier()
     planner.get_work(reset=True)
     l0 = planner.launch_count()
@@ -505,7 +507,7 @@ def run_sweep5(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        winner = sd.run_sweep(planner, shard, outs)
+        winner = sd.run_sweep(planner, shard, outs, options=sweep_opt)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -558,7 +560,7 @@ def run_sweep5(args):
                                         "ADMM path, %d rank(s), arg-min of the batch at the end (spectral_sweep_argmin)" if args.config == 4 else
                                         "config5: %d-scenario sweep, config-4 generator (mixed trp+cub, K in [4,14], seed 20230603), contiguous "
                                         "global-index shards over %d rank(s), one NCCL argmin exchange per pass (spectral_sweep_argmin)") % (total, world),
-                           "total_scenarios": total, "chunk": sd.CHUNK, "scenarios_this_rank": n_local,
+                           "total_scenarios": total, "chunk": sd.CHUNK, "shared_kkt": bool(args.shared), "scenarios_this_rank": n_local,
                            "l2": "inputs larger than L2: %.1f GB resident per rank" % (n_local * 8.1e3 / 1e9),
                            "winner": {"cost": winner["cost"], "index": winner["index"], "rank": winner["rank"], "K": winner["K"]},
                            "solved_fraction": work["solved"] / max(work["scenarios"], 1.0), "generation_s_untimed": gen_s,
@@ -638,6 +640,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="steps in flight (one handle + CUDA stream each; 0: the workload's default)")
     ap.add_argument("--config", type=int, default=2, help="2: BASELINE configs[1] (default, the metric's config); 3: configs[2] (shared-KKT, DMMA); 4: configs[3] (262 144 mixed trp+cub, variable structure); 5: configs[4] (1 M sweep, strong scaling)")
     ap.add_argument("--total", type=int, default=0, help="config 4 / 5: scenarios in the batch / sweep (multiple of 8192; default 262144 / 1048576)")
+    ap.add_argument("--shared", action="store_true", help="config 4 / 5: route the K <= 8 class through the shared-KKT tile kernel (SpectralOptions.shared_kkt = 1)")
     ap.add_argument("--no-shared", action="store_true", help="config 3 through the per-scenario kernels (A/B of the shared-KKT path)")
     ap.add_argument("--groups", type=int, default=8, help="config 3: number of shared-KKT groups (1, 8, 64)")
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))

@@ -156,6 +156,28 @@ __global__ void k_broadcast_corridor(int *K, SpectralCube *segs, int *cstatus, i
   for (int k = 0; k < n; k++) segs[(size_t)b * k_max + k] = segs[k];
 }
 
+// k_qpa<8> with the finish deferred (qp_shared.cuh: qpa_handoff): the CTA hands the end state of each scenario to k_qps_finish,
+// which polishes 16 scenarios per SM at a time instead of one warp of a 4-warp CTA while the other three wait.
+__global__ void __launch_bounds__(2 * QpdLayout<8>::TA, 2) k_qpa8_deferred(const QpsArgs A) {
+  extern __shared__ __align__(16) double qpd_smem[];
+  __shared__ int s_slot;
+  const QpArgs &a = A.q;
+  for (;;) {
+    if (threadIdx.x == 0) s_slot = atomicAdd(a.next, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    __syncthreads();
+    if (slot >= *a.count) return;
+    qpa_cta_body<8>(a, slot, threadIdx.x, qpd_smem, []() { __syncthreads(); },
+                    [](int axis) {
+                      if (axis == 0) asm volatile("bar.sync 1, %0;" ::"n"(QpdLayout<8>::TA) : "memory");
+                      else asm volatile("bar.sync 2, %0;" ::"n"(QpdLayout<8>::TA) : "memory");
+                    },
+                    true);
+    qpa_handoff(A, slot, threadIdx.x, blockDim.x, qpd_smem);
+  }
+}
+
 // ------------------------------------------------------------------ shared-KKT path (qp_shared.cuh)
 // structure key of a scenario of the K <= 8 class: (K, the bit patterns of t_k, the weights when they are per scenario)
 __global__ void k_qps_keys(const int *cstatus, const int *K, const SpectralCube *segs, int k_max, const double *weights, int wstride, int B,
@@ -380,6 +402,7 @@ struct spectral_handle {
   int classes_timed = 0;    // solver classes launched per call (k_max dependent)
   int corridor_smem = 0;    // dynamic shared memory the corridor kernel is opted in for on this handle's device
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
+  bool defer_finish = false; // SPECTRAL_DEFER_FINISH=1: K <= 8 class: status / polish / outputs in k_qps_finish instead of in the ADMM CTA
   bool force_lanes = false; // SPECTRAL_FORCE_LANES=1: k_qp<8|16> (lane per segment, block-tridiagonal solve) for every class
   bool legacy_qps = false;  // SPECTRAL_LEGACY_QPS=1: the two-warp shared-KKT tile kernel instead of the four-warp one
 };
@@ -420,6 +443,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   { const char *e = getenv("SPECTRAL_LEGACY_QPD"); h->legacy_qpd = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_LEGACY_QPS"); h->legacy_qps = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_FORCE_LANES"); h->force_lanes = e && e[0] == '1'; }
+  { const char *e = getenv("SPECTRAL_DEFER_FINISH"); h->defer_finish = e && e[0] == '1'; }
   *out = h;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -544,7 +568,14 @@ static cudaError_t launch_qpa(spectral_handle *h, const QpArgs &qa, int B, cudaS
 }
 
 // Shared-KKT path for the K <= 8 class: structure keys -> sort -> tiles of <= 8 scenarios -> prepare -> tile ADMM (DMMA) -> finish
+static int ensure_qps_buffers(spectral_handle *h);
+static int launch_qps_impl(spectral_handle *h, const QpArgs &qa, const int *cstatus, int B, const SpectralInputs *in, cudaStream_t st);
 static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, int B, const SpectralInputs *in, cudaStream_t st) {
+  const size_t Bm = (size_t)h->max_batch;
+  { const int rc = ensure_qps_buffers(h); if (rc) return rc; }
+  return launch_qps_impl(h, qa, cstatus, B, in, st);
+}
+static int ensure_qps_buffers(spectral_handle *h) {
   const size_t Bm = (size_t)h->max_batch, km = (size_t)h->k_max;
   if (!h->qs_keys) {
     CK(cudaMalloc(&h->qs_keys, Bm * 8)); CK(cudaMalloc(&h->qs_keys2, Bm * 8));
@@ -562,6 +593,10 @@ static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, 
     h->qs_cub_bytes = t1 > t2 ? (t1 > t3 ? t1 : t3) : (t2 > t3 ? t2 : t3);
     CK(cudaMalloc(&h->qs_cub, h->qs_cub_bytes));
   }
+  return SPECTRAL_SUCCESS;
+}
+static int launch_qps_impl(spectral_handle *h, const QpArgs &qa, const int *cstatus, int B, const SpectralInputs *in, cudaStream_t st) {
+  const size_t Bm = (size_t)h->max_batch;
   int *head = h->qs_tmp, *gstart = h->qs_tmp + Bm, *flag = h->qs_tmp + 2 * Bm, *tidx = h->qs_tmp + 3 * Bm;
   int *tile_start = h->qs_tile, *tile_count = h->qs_tile + Bm;
   const int nb = (B + 255) / 256;
@@ -600,6 +635,25 @@ static int launch_qps(spectral_handle *h, const QpArgs &qa, const int *cstatus, 
   }
   k_qps_finish<<<pf_blocks, 64, sm_pf, st>>>(A);
   h->launches += 8;
+  CK(cudaGetLastError());
+  return SPECTRAL_SUCCESS;
+}
+
+// K <= 8 class on the anchor kernel with the finish deferred to k_qps_finish (each scenario its own tile)
+static int launch_qpa8_deferred(spectral_handle *h, const QpArgs &qa, int B, cudaStream_t st) {
+  { const int rc = ensure_qps_buffers(h); if (rc) return rc; }
+  QpsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.q = qa; A.q.lu = h->qs_lu;
+  A.blk = h->qs_blk; A.qv = h->qs_qv; A.wrows = h->qs_w; A.xout = h->qs_x; A.st = h->qs_st;
+  const size_t smem = QpdLayout<8>::BYTES;
+  CK(cudaFuncSetAttribute(k_qpa8_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+  k_qpa8_deferred<<<grid, 2 * QpdLayout<8>::TA, smem, st>>>(A);
+  const size_t sm_pf = 2 * (size_t)QP_SMEM_PER_WARP;
+  CK(cudaFuncSetAttribute(k_qps_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
+  k_qps_finish<<<(B + 3) / 4, 64, sm_pf, st>>>(A);
+  h->launches += 2;
   CK(cudaGetLastError());
   return SPECTRAL_SUCCESS;
 }
@@ -703,6 +757,7 @@ static int solve_device_impl(spectral_handle_t *h, int variant, int B, int N, in
       else CK((launch_qp<16, 2>(h, qa, B, cs)));
     }
     else if (cls == 0 && opt.shared_kkt) { const int rc = launch_qps(h, qa, h->cstatus, B, in, cs); if (rc) return rc; }
+    else if (cls == 0 && h->defer_finish && !h->legacy_qpd && out->lu == nullptr) { const int rc = launch_qpa8_deferred(h, qa, B, cs); if (rc) return rc; }
     else if (cls == 0) CK((h->legacy_qpd ? launch_qpd<8>(h, qa, B, cs) : launch_qpa<8>(h, qa, B, cs)));
     else if (cls == 1) CK((h->legacy_qpd ? launch_qpd<10>(h, qa, B, cs) : launch_qpa<10>(h, qa, B, cs)));
     else if (cls == 2) CK((launch_qpd<12>(h, qa, B, cs)));

@@ -313,8 +313,10 @@ SP_DEV_NOINLINE int qpa_check(const QpArgs &a, int slot, int tid, double *smem, 
 
 // slot: index of the scenario in this class' list.  tid in [0, 2 TA).  smem: QpdLayout<KC>::BYTES, 16-byte aligned.
 // sync_axis(axis) synchronises the TA threads of one axis.
+// defer: leave the final status / polish / outputs (qpd_control_finish) to a later kernel: the scalars it needs are published
+// in red[0..3] = (c_scale, rhobar, state, iterations), everything else already sits in the control slots of shared memory.
 template <int KC, typename SyncFn, typename SyncAxisFn>
-SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncFn sync_cta, SyncAxisFn sync_axis_fn) {
+SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncFn sync_cta, SyncAxisFn sync_axis_fn, bool defer = false) {
   using L = QpdLayout<KC>;
   static_assert(L::ROWFULL && L::TA == 32 * ((KC + QPA_SPW - 1) / QPA_SPW), "anchor layout: five segments per warp, whole rows of G");
   constexpr int N = L::N, LPA = L::LPA, STR = L::STR, TA = L::TA;
@@ -426,6 +428,11 @@ SP_DEV void qpa_cta_body(const QpArgs &a, int slot, int tid, double *smem, SyncF
       ctlw[QP_SM_RHO * STR + ooff] = io.rho[s];
     }
     if (isvar) smx[L::O_XR + QPD_CP + v] = io.xv;
+  }
+  if (defer) {
+    if (tid == 0) { red[0] = c_scale; red[1] = rhobar; red[2] = (double)state; red[3] = (double)iters; }
+    sync_cta();
+    return;
   }
   sync_cta();
   if (warp != 0) return;

@@ -492,6 +492,44 @@ SP_DEV void qps_tile_body(const QpsArgs &A, int tile, int cta, int tid, double *
   if (lane == 0) Bw.rhobar = rhobar;
 }
 
+// Deferred finish of the per-scenario anchor kernel (K <= 8 class): the CTA that ran the ADMM loop of one scenario hands its end
+// state to k_qps_finish in the formats of the shared-KKT path -- the scenario is its own "tile" (tile id = its slot in the class
+// list): structure block, (l, u) rows, q, w rows, relaxed x, state.  All of it sits in the control slots of the CTA's shared
+// memory (QpdLayout<8>: slots [slot][segment] with stride 8, lane store, XR) when the loop ends.
+SP_DEV void qpa_handoff(const QpsArgs &A, int slot, int tid, int nthreads, const double *smem) {
+  using L = QpdLayout<QPS_KC>;
+  static_assert(L::STR == 8 && L::LPA == 8, "control slots of the K <= 8 layout");
+  const QpArgs &a = A.q;
+  const int b = a.list[slot];
+  const double *red = smem + L::O_RED;
+  const int *eqm = (const int *)(smem + L::O_EQ);
+  for (int e = tid; e < 2 * 8 * QP_ROWS; e += nthreads) {
+    const int axis = e / (8 * QP_ROWS), rem = e - axis * 8 * QP_ROWS, seg = rem / QP_ROWS, r = rem - seg * QP_ROWS;
+    const double *ctl = smem + axis * L::AXIS + L::O_CTRL;
+    QpsTileBlk &Bk = A.blk[2 * slot + axis];
+    Bk.rho[r][seg] = ctl[(QP_SM_RHO + r) * 8 + seg];
+    Bk.P[r][seg] = ctl[(QP_SM_P + r) * 8 + seg];
+    double *lu = a.lu + ((((size_t)b * 2 + axis) * a.k_max + seg) * QP_ROWS + r) * 2;
+    lu[0] = ctl[(QP_SM_L + r) * 8 + seg];
+    lu[1] = ctl[(QP_SM_U + r) * 8 + seg];
+    A.wrows[(((size_t)b * 2 + axis) * 8 + seg) * QP_ROWS + r] = ctl[(QP_SM_W + r) * 8 + seg];
+  }
+  for (int e = tid; e < 2 * 8; e += nthreads) {
+    const int axis = e >> 3, seg = e & 7;
+    const double *d = smem + axis * L::AXIS + L::O_LS + QPD_LS * seg;
+    const double *xr = smem + axis * L::AXIS + L::O_XR + QPD_CP + 6 * seg;
+    QpsTileBlk &Bk = A.blk[2 * slot + axis];
+    Bk.t[seg] = d[0]; Bk.tp[seg] = d[1]; Bk.tn[seg] = d[2];
+    double *qs = A.qv + (((size_t)b * 2 + axis) * 8 + seg) * 6;
+    double *dx = A.xout + ((size_t)b * 2 + axis) * QPS_N + 6 * seg;
+#pragma unroll
+    for (int j = 0; j < 6; j++) { qs[j] = d[3 + j]; Bk.sig[seg][j] = d[9 + j]; Bk.cD[seg][j] = d[15 + j]; dx[j] = xr[j]; }
+    Bk.eqmask[seg] = eqm[axis * 8 + seg];
+    if (seg == 0) { Bk.c = red[0]; Bk.rhobar = red[1]; Bk.K = a.K[b]; Bk.pad = 0; }
+  }
+  if (tid == 0) { A.st[4 * b + 0] = (int)red[2]; A.st[4 * b + 1] = (int)red[3]; A.st[4 * b + 2] = slot; A.st[4 * b + 3] = 0; }
+}
+
 // k_qps_prepare body: one warp = two scenarios of the K <= 8 class (16 lanes each: 8 segment lanes per axis).  K3 assembly
 // (l, u -> a.lu, q -> qv), and for a tile's first scenario the Ruiz scaling / rho / P of the tile.
 SP_DEV void qps_prepare_body(const QpsArgs &A, const int *leader_tile, int warp_global, int lane, double *sm) {

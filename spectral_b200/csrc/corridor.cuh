@@ -233,7 +233,13 @@ SP_DEV void std_sort_by_beg_t(SortView v, int n) {
 
 // num / delta, IEEE.  A zero numerator (flat bounds: the common case) gives a zero of the numerator's sign for any
 // positive delta; answering it directly keeps the division's slow path (taken for zero operands) out of the way.
-SP_DEV double slope_div(double num, double delta) { return (num == 0.0 && delta > 0.0) ? num : num / delta; }
+// The division itself always runs on a non-zero numerator (1.0 stands in for the zeros), so that no lane of the warp ever
+// drags the others through the out-of-line special-case routine of the double-precision division.
+SP_DEV double slope_div(double num, double delta) {
+  const bool zero = num == 0.0 && delta > 0.0;
+  const double q = (zero ? 1.0 : num) / delta;
+  return zero ? num : q;
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1: one warp, one region.  Returns the cube count written to `out` (shared) or -1 (capacity).
@@ -398,24 +404,41 @@ SP_DEV void corridor_cta_body(const CorridorArgs &a, int b, int warp, int lane, 
 
   // inside counts of this region's cubes: lanes over knots, popc(ballot) (solve_3d.cc:529-584)
   if (n > 0) {
-    for (int k = 0; k < n; k++) {
-      const SpectralCube c = cubes[k];
-      // The first and the third edge test of point_inside are  -(t - beg_t) a1  and  -(t - end_t) a3  (their other terms are
-      // multiplied by the reference's (beg_t - beg_t) / (end_t - end_t) = 0).  With a1 > 0 and a3 < 0 -- every cube whose upper
-      // face lies above its lower face -- they have strictly opposite signs for every knot outside [beg_t, end_t], i.e. such
-      // a knot is never inside: only the cube's own knots need the test.  Other cubes take the full scan.
+    // The first and the third edge test of point_inside are  -(t - beg_t) a1  and  -(t - end_t) a3  (their other terms are
+    // multiplied by the reference's (beg_t - beg_t) / (end_t - end_t) = 0).  With a1 > 0 and a3 < 0 -- every cube whose upper
+    // face lies above its lower face -- they have strictly opposite signs for every knot outside [beg_t, end_t], i.e. such
+    // a knot is never inside: only the cube's own knots need the test.  After the split a cube spans at most 11 knots, so
+    // TWO cubes share one ballot (lanes 0-15: cube k, lanes 16-31: cube k + 1).  Any other cube takes the full scan.
+    for (int k = 0; k < n; k += 2) {
+      const int half = lane >> 4, l16 = lane & 15, kk = k + half;
+      const bool have = kk < n;
+      const SpectralCube c = cubes[have ? kk : k];
       const double a1 = c.upp_bias - c.down_bias;
       const double a3 = c.down_skew * a.delta + c.down_bias - c.upp_skew * a.delta - c.upp_bias;
-      const bool local = a1 > 0.0 && a3 < 0.0 && c.beg_t >= 0 && c.end_t >= c.beg_t && c.end_t < N;
-      const int lo = local ? c.beg_t : 0, hi = local ? c.end_t + 1 : N;
-      int total = 0;
-      for (int base = lo; base < hi; base += 32) {
-        int i = base + lane;
-        int in = 0;
-        if (i < hi) in = point_inside(c, sref[i], lref[i], (double)i, a.delta);
-        total += sp_popc(sp_ballot(in));
+      const int len = c.end_t - c.beg_t + 1;
+      const bool fast = have && a1 > 0.0 && a3 < 0.0 && c.beg_t >= 0 && len >= 1 && len <= 16 && c.end_t < N;
+      int in = 0;
+      if (fast && l16 < len) {
+        const int i = c.beg_t + l16;
+        in = point_inside(c, sref[i], lref[i], (double)i, a.delta);
       }
-      if (lane == 0) cnt[k] = total;
+      const unsigned m = sp_ballot(in);
+      if (fast && l16 == 0) cnt[kk] = sp_popc(half ? (m >> 16) : (m & 0xffffu));
+      // the full scan for the cubes of this pair that are not "fast" (warp-uniform: the flags of lanes 0 and 16)
+      const int fa = sp_shfl_i(fast ? 1 : 0, 0), fb = sp_shfl_i(fast ? 1 : 0, 16);
+      for (int which = 0; which < 2; which++) {
+        const int kf = k + which;
+        if ((which == 0 ? fa : fb) || kf >= n) continue;
+        const SpectralCube cf = cubes[kf];
+        int total = 0;
+        for (int base = 0; base < N; base += 32) {
+          const int i = base + lane;
+          int inf = 0;
+          if (i < N) inf = point_inside(cf, sref[i], lref[i], (double)i, a.delta);
+          total += sp_popc(sp_ballot(inf));
+        }
+        if (lane == 0) cnt[kf] = total;
+      }
     }
   }
   sync_cta();

@@ -180,8 +180,11 @@ __global__ void __launch_bounds__(2 * QpdLayout<8>::TA, 2) k_qpa8_deferred(const
 
 // ------------------------------------------------------------------ shared-KKT path (qp_shared.cuh)
 // structure key of a scenario of the K <= 8 class: (K, the bit patterns of t_k, the weights when they are per scenario)
+// `hint` (may be null): st[4 b + 3] of a first prepare pass run with the interval pre-check forced on = "this corridor is provably
+// empty".  It is mixed into the key, so that tiles are homogeneous in it: members that converge in a few hundred iterations no
+// longer idle in a tile until an infeasible member has burnt its 5000 (the hint decides tile membership only, never a status).
 __global__ void k_qps_keys(const int *cstatus, const int *K, const SpectralCube *segs, int k_max, const double *weights, int wstride, int B,
-                           unsigned long long *keys, int *ids, int *leader_tile) {
+                           unsigned long long *keys, int *ids, int *leader_tile, const int *hint) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   unsigned long long h = ~0ull;
@@ -193,6 +196,7 @@ __global__ void k_qps_keys(const int *cstatus, const int *K, const SpectralCube 
     for (int k = 0; k < K[b]; k++) mix((unsigned long long)__double_as_longlong(segs[(size_t)b * k_max + k].t));
     if (wstride)
       for (int i = 0; i < 10; i++) mix((unsigned long long)__double_as_longlong(weights[(size_t)b * 10 + i]));
+    if (hint) mix(hint[4 * b + 3] ? 0x5bd1e995ull : 0x1b873593ull);
     if (h == ~0ull) h = 0x1234567ull;
   }
   keys[b] = h; ids[b] = b; leader_tile[b] = -1;
@@ -404,6 +408,7 @@ struct spectral_handle {
   bool legacy_qpd = false;  // SPECTRAL_LEGACY_QPD=1: the round-1 full-row kernels for K <= 10 (A/B measurements)
   bool defer_finish = false; // SPECTRAL_DEFER_FINISH=1: K <= 8 class: status / polish / outputs in k_qps_finish instead of in the ADMM CTA
   bool force_lanes = false; // SPECTRAL_FORCE_LANES=1: k_qp<8|16> (lane per segment, block-tridiagonal solve) for every class
+  bool qps_nohint = false;  // SPECTRAL_QPS_NOHINT=1: shared-KKT tiles keyed by structure only (no feasibility hint in the key)
   bool legacy_qps = false;  // SPECTRAL_LEGACY_QPS=1: the two-warp shared-KKT tile kernel instead of the four-warp one
 };
 
@@ -442,6 +447,7 @@ extern "C" int spectral_create(int device, int max_batch, int n_max, int r_max, 
   h->device = device; h->max_batch = max_batch; h->n_max = n_max; h->r_max = r_max; h->k_max = k_max;
   { const char *e = getenv("SPECTRAL_LEGACY_QPD"); h->legacy_qpd = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_LEGACY_QPS"); h->legacy_qps = e && e[0] == '1'; }
+  { const char *e = getenv("SPECTRAL_QPS_NOHINT"); h->qps_nohint = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_FORCE_LANES"); h->force_lanes = e && e[0] == '1'; }
   { const char *e = getenv("SPECTRAL_DEFER_FINISH"); h->defer_finish = e && e[0] == '1'; }
   *out = h;
@@ -601,7 +607,22 @@ static int launch_qps_impl(spectral_handle *h, const QpArgs &qa, const int *csta
   int *tile_start = h->qs_tile, *tile_count = h->qs_tile + Bm;
   const int nb = (B + 255) / 256;
   CK(cudaMemsetAsync(h->qs_misc, 0, 8, st));
-  k_qps_keys<<<nb, 256, 0, st>>>(cstatus, qa.K, qa.segs, h->k_max, qa.weights, qa.wstride, B, h->qs_keys, h->qs_ids, h->qs_leader);
+  const size_t sm_pf = 2 * (size_t)QP_SMEM_PER_WARP;
+  const int pf_blocks = (B + 3) / 4;  // two scenarios per warp, two warps per block
+  CK(cudaFuncSetAttribute(k_qps_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
+  if (!h->qps_nohint) {
+    // hint pass: the K3 assembly of every scenario of the class with the interval pre-check forced on, no tile yet (leader = -1)
+    QpsArgs Hh;
+    memset(&Hh, 0, sizeof(Hh));
+    Hh.q = qa; Hh.q.lu = h->qs_lu; Hh.q.opt.precheck = 1;
+    if (!(Hh.q.opt.precheck_margin > 0.0)) Hh.q.opt.precheck_margin = 1e-3;
+    Hh.blk = h->qs_blk; Hh.qv = h->qs_qv; Hh.wrows = h->qs_w; Hh.xout = h->qs_x; Hh.st = h->qs_st;
+    CK(cudaMemsetAsync(h->qs_leader, 0xFF, (size_t)B * 4, st));
+    k_qps_prepare<<<pf_blocks, 64, sm_pf, st>>>(Hh, h->qs_leader);
+    h->launches++;
+  }
+  k_qps_keys<<<nb, 256, 0, st>>>(cstatus, qa.K, qa.segs, h->k_max, qa.weights, qa.wstride, B, h->qs_keys, h->qs_ids, h->qs_leader,
+                                h->qps_nohint ? nullptr : h->qs_st);
   size_t tb = h->qs_cub_bytes;
   CK(cub::DeviceRadixSort::SortPairs(h->qs_cub, tb, h->qs_keys, h->qs_keys2, h->qs_ids, h->qs_ids2, B, 0, 64, st));
   k_qps_heads<<<nb, 256, 0, st>>>(h->qs_keys2, B, head);
@@ -616,11 +637,8 @@ static int launch_qps_impl(spectral_handle *h, const QpArgs &qa, const int *csta
   A.tile_start = tile_start; A.tile_count = tile_count; A.n_tiles = h->qs_misc; A.sorted = h->qs_ids2; A.tile_next = h->qs_misc + 1;
   A.fs_scratch = h->qs_fs;
   A.blk = h->qs_blk; A.qv = h->qs_qv; A.wrows = h->qs_w; A.xout = h->qs_x; A.st = h->qs_st;
-  const size_t sm_pf = 2 * (size_t)QP_SMEM_PER_WARP;
-  CK(cudaFuncSetAttribute(k_qps_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
   CK(cudaFuncSetAttribute(k_qps_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pf));
   CK(cudaFuncSetAttribute(k_qps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QpsSmem::BYTES));
-  const int pf_blocks = (B + 3) / 4;  // two scenarios per warp, two warps per block
   k_qps_prepare<<<pf_blocks, 64, sm_pf, st>>>(A, h->qs_leader);
   const int tiles_max = B;
   if (h->legacy_qps) {   // SPECTRAL_LEGACY_QPS=1: the two-warp tile layout (A/B measurements)

@@ -29,6 +29,9 @@
 #ifndef QPA_GRP
 #define QPA_GRP(N) (((N) % 24 == 0) ? 24 : (((N) % 20 == 0) ? 20 : 12))  // doubles of g in flight per group in S3
 #endif
+#ifndef QPA_WRAP_SHFL
+#define QPA_WRAP_SHFL 0   // 1: neighbour shuffles with wrap-around instead of shfl.up + boundary masks (measured: 86.7 k vs 87.2 k solves/s, not taken)
+#endif
 #ifndef QPA_FENCE
 #define QPA_FENCE 0   // scheduling fences between the load runs and the arithmetic (measured: 81.5 k solves/s with, 82.6 k without)
 #endif
@@ -62,6 +65,16 @@ SP_DEV void qpa_map(int ta, int &seg, int &i, bool &isvar) {
 // Arithmetic ordered as qpd_block1's S2.
 template <bool CHECK_ORDER>
 SP_DEV double qpa_gather(const double vv[5], int lane, int jsrc, double tkv, double f0, double f1, double f2, double rest) {
+#if QPA_WRAP_SHFL
+  // Neighbours by index shuffle with wrap-around: lanes 0..2 read lanes 29..31, which hold no live velocity / acceleration /
+  // jerk row (lanes 30, 31 are idle, lane 29 is control point 5 of its segment: its jerk slot does not exist), i.e. rho = 0
+  // and value 0 -- like the neighbour across any segment boundary.  No boundary masks needed.
+  const int l1 = (lane + 31) & 31, l2 = (lane + 30) & 31, l3 = (lane + 29) & 31;
+  const double g1a = sp_shfl(vv[1], l1);
+  const double g2b = sp_shfl(vv[2], l1), g2a = sp_shfl(vv[2], l2);
+  const double g3c = sp_shfl(vv[3], l1), g3b = sp_shfl(vv[3], l2), g3a = sp_shfl(vv[3], l3);
+  const double c0 = sp_shfl(vv[4], jsrc), c1 = sp_shfl(vv[4], jsrc + 1), c2 = sp_shfl(vv[4], jsrc + 2);
+#else
   const double u11 = sp_shfl_up(vv[1], 1, 32);
   const double u21 = sp_shfl_up(vv[2], 1, 32), u22 = sp_shfl_up(vv[2], 2, 32);
   const double u31 = sp_shfl_up(vv[3], 1, 32), u32 = sp_shfl_up(vv[3], 2, 32), u33 = sp_shfl_up(vv[3], 3, 32);
@@ -71,6 +84,7 @@ SP_DEV double qpa_gather(const double vv[5], int lane, int jsrc, double tkv, dou
   const double g1a = lane >= 1 ? u11 : 0.0;
   const double g2b = lane >= 1 ? u21 : 0.0, g2a = lane >= 2 ? u22 : 0.0;
   const double g3c = lane >= 1 ? u31 : 0.0, g3b = lane >= 2 ? u32 : 0.0, g3a = lane >= 3 ? u33 : 0.0;
+#endif
   if (CHECK_ORDER) {  // summation order of qpd_gather (the termination check's A' y and A' delta y)
     double g = tkv * vv[0];
     g += 5.0 * (g1a - vv[1]);
